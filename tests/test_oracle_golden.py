@@ -1,0 +1,76 @@
+"""CPU: the numpy oracle (oracle/distortion_oracle.py) against the reference-generated goldens."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import distortion_oracle as orc
+from tests import goldenio
+
+
+@pytest.mark.parametrize("name", goldenio.names())
+def test_compute_metrics_matches_reference_golden(name):
+    c = goldenio.load(name)
+    got = orc.compute_metrics(c["ref"], c["tst"], c["valid"], ref_nodata=c["ref_nodata"],
+                              tst_nodata=c["tst_nodata"], extras=False)
+    want = c["compute_metrics"]
+    assert set(got) == set(want)
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, int):
+            assert isinstance(g, int) and g == w, k
+        else:
+            # same numpy ops in the same order: expect bit equality, not just 1e-6
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+
+
+@pytest.mark.parametrize("name", goldenio.names())
+def test_sam_sid_lmse_matches_reference_golden(name):
+    c = goldenio.load(name)
+    got = orc.compute_sam_sid_lmse_caseB(c["ref"], c["tst"], c["valid"], ref_nodata=c["ref_nodata"],
+                                         tst_nodata=c["tst_nodata"])
+    for k, w in c["sam_sid_lmse"].items():
+        g = got[k]
+        assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+
+
+@pytest.mark.parametrize("name", goldenio.names())
+def test_error_max8_matches_reference_golden(name):
+    c = goldenio.load(name)
+    for n, e in enumerate(c["err8"]):
+        got = orc.error_max8(c["ref"], c["tst"], e["cap_g"], e["cap_z"], ref_nodata=c["ref_nodata"],
+                             tst_nodata=c["tst_nodata"])
+        assert np.array_equal(got["err8_g"], c["planes"][f"err8_{n}_g"])
+        assert np.array_equal(got["valid"].astype(np.uint8), c["planes"][f"err8_{n}_mask"])
+        assert e["name_g"] == f"recon_ERR8_0_{got['cap_g']}.tif"
+        assert float(e["tags_g"]["STATISTICS_MEAN"]) == got["mean_g"]
+        assert float(e["tags_g"]["STATISTICS_STDDEV"]) == got["std_g"]
+        if e["cap_z"] is not None:
+            assert np.array_equal(got["err8_z"], c["planes"][f"err8_{n}_z"])
+            assert e["name_z"] == f"recon_ERR8_0_{got['cap_z']}.tif"
+        # the LUT restatement reproduces the float32 chain for every integer error
+        lut = orc.err8_lut(e["cap_g"])
+        err_i = got["err"].astype(np.int64)
+        assert np.array_equal(lut[np.minimum(err_i, e["cap_g"])], got["err8_g"])
+
+
+def test_extras_self_consistency():
+    c = goldenio.load("a_gauss")
+    got = orc.compute_metrics(c["ref"], c["tst"], hist_bins=256)
+    for i in range(1, 5):
+        h = got[f"hist_b{i}"]
+        k = np.arange(256)
+        assert h.sum() == got["n_valid"]
+        assert (h * k * k).sum() == got[f"sse_b{i}"]
+        assert (h * k).sum() / got["n_valid"] == got[f"mae_b{i}"]
+        assert np.nonzero(h)[0].max() == got[f"maxerr_b{i}"]
+
+
+def test_gaussian_taps_are_scipy_taps():
+    from scipy.ndimage import gaussian_filter
+    imp = np.zeros(41); imp[20] = 1.0
+    resp = gaussian_filter(imp, sigma=1.5, truncate=3.5, mode="reflect")
+    taps = orc.gaussian_taps()
+    assert taps.size == 11
+    assert np.allclose(resp[15:26], taps, rtol=0, atol=1e-17)
+    assert abs(taps[5] - 0.266011724862) < 1e-11 and abs(taps[0] - 0.001028380084) < 1e-11
