@@ -1,0 +1,151 @@
+// Shared host/device helpers for libdm_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dm_b200.h"
+
+namespace dm {
+
+// ---- host side --------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);           // records dm_last_error(), returns code
+int cuda_fail(cudaError_t e, const char* what);     // DM_ECUDA with the CUDA error text
+int sm_count();                                     // SMs of the current device (cached), <0 on error
+
+#define DM_CUDA(expr)                                              \
+  do {                                                             \
+    cudaError_t dm_e_ = (expr);                                    \
+    if (dm_e_ != cudaSuccess) return ::dm::cuda_fail(dm_e_, #expr); \
+  } while (0)
+
+#define DM_LAUNCH_CHECK(name)                                       \
+  do {                                                              \
+    cudaError_t dm_e_ = cudaGetLastError();                         \
+    if (dm_e_ != cudaSuccess) return ::dm::cuda_fail(dm_e_, name);  \
+  } while (0)
+
+static inline int elem_bytes(int dtype) { return dtype == DM_U8 ? 1 : 2; }
+
+// launchers implemented in the kernel translation units
+int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, int hist_bins,
+                       uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, cudaStream_t s);
+int launch_validity(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out,
+                    int64_t* counts, cudaStream_t s);
+int spectral_nblocks();
+int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_out,
+                    const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                    const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z,
+                    int want_sam, int want_sid, double* spectral_out, cudaStream_t s);
+int sobel_nblocks();
+int ssim_nblocks();
+int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0,
+                 int64_t img_rows, double* out, cudaStream_t s);
+int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t row_end,
+                      int64_t img_row0, int64_t img_rows, double* out, cudaStream_t s);
+int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands, int64_t rows,
+                      int64_t width, cudaStream_t s);
+
+// ---- device side ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// streaming 128/64/32-bit loads: read-only path, do not allocate in L1 (data is touched once)
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream4(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// sample decode: element j (0/1) of a 32-bit word holding two 16-bit samples
+template <int DT>
+__device__ __forceinline__ int sample16(uint32_t w, int j) {
+  if (DT == DM_I16) return j ? ((int)w >> 16) : ((int)(w << 16) >> 16);
+  return j ? (int)(w >> 16) : (int)(w & 0xffffu);
+}
+
+template <int DT, typename T>
+__device__ __forceinline__ int sample_at(const T* p, int64_t i) {
+  return (int)p[i];
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide reductions through a small shared scratch (>= 32 x 8 bytes).  All threads call.
+// Result valid in thread 0.  blockDim.x may be any size <= 1024 (partial last warp allowed
+// only if every thread of the block participates, which __shfl with full mask requires:
+// callers keep blockDim.x a multiple of 32).
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_ll(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? scratch[lane] : 0;
+    v = warp_sum_ll(v);
+  }
+  return v;
+}
+__device__ __forceinline__ long long block_max_ll(long long v, long long* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max_ll(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? scratch[lane] : (long long)0x8000000000000000ll;
+    v = warp_max_ll(v);
+  }
+  return v;
+}
+__device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_f64(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? scratch[lane] : 0.0;
+    v = warp_sum_f64(v);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void atomic_add_i64(int64_t* p, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void atomic_max_i64(int64_t* p, long long v) {
+  atomicMax(reinterpret_cast<long long*>(p), v);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dm

@@ -1,0 +1,94 @@
+// libdm_b200.so: C-ABI entry points (include/dm_b200.h), error reporting and device queries.
+#include <cstdarg>
+#include <cstdio>
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(DM_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return -cuda_fail(e, "cudaGetDevice");
+  if (dev != cached_dev) {
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return -cuda_fail(e, "cudaDeviceGetAttribute");
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" {
+
+int dm_abi_version(void) { return DM_ABI_VERSION; }
+const char* dm_last_error(void) { return g_err; }
+int dm_device_sm_count(void) { return sm_count(); }
+
+int dm_validity(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts_out,
+                void* stream) {
+  if (!p) return fail(DM_EARG, "dm_validity: null pair");
+  return launch_validity(*p, valid_in, plane_out, counts_out, static_cast<cudaStream_t>(stream));
+}
+
+int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, int32_t hist_bins,
+                   uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_fused_stats: null pair");
+  return launch_fused_stats(*p, plane, plane_bit, hist_bins, flags, sums, maxs, hist,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int dm_spectral_nblocks(void) { return spectral_nblocks(); }
+
+int dm_spectral(const dm_pair_t* p, const uint8_t* plane, uint16_t* errmax_out, const uint8_t* lut_g,
+                int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z, int32_t cap_z,
+                uint8_t* err8_z, int64_t* hist8_z, int32_t want_sam, int32_t want_sid,
+                double* spectral_out, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_spectral: null pair");
+  return launch_spectral(*p, plane, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
+                         hist8_z, want_sam, want_sid, spectral_out, static_cast<cudaStream_t>(stream));
+}
+
+int dm_sobel_nblocks(void) { return sobel_nblocks(); }
+
+int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,
+                  int64_t img_rows, double* out, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_sobel_lmse: null pair");
+  return launch_sobel(*p, row_begin, row_end, img_row0, img_rows, out, static_cast<cudaStream_t>(stream));
+}
+
+int dm_ssim_nblocks(void) { return ssim_nblocks(); }
+
+int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
+                  int64_t img_row0, int64_t img_rows, double* out, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_ssim_gauss: null pair");
+  return launch_ssim_gauss(*p, data_range, row_begin, row_end, img_row0, img_rows, out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands, int64_t rows,
+                  int64_t width, void* stream) {
+  return launch_bip_to_bsq(src, dst, elem_bytes, bands, rows, width, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// Per-pixel spectral pass: one sweep over the spectral axis of every pixel.
+//
+//   error quicklook   /root/reference/tools/quicklooks.py:123-150  max_b |A-B| -> 8-bit via LUT
+//   SAM               /root/reference/tools/run_codec.py:328-332
+//   SID               /root/reference/tools/run_codec.py:334-339
+//
+// SAM's dot / |a|^2 / |r|^2 are exact int64 sums (<= 180*65535^2 < 2^53), so cos(angle) is
+// reproduced bit-for-bit with correctly rounded sqrt / mul / div; acos and log are libdevice
+// (<= 2 ulp).  SID follows the reference's float64 expressions term by term.  Floating-point
+// partial sums are written per block in block order so that the host reduction is deterministic.
+//
+// The ERR8 scaling is a float32 chain in the reference (clip((e-0)/(cap+1e-9),0,1)*255 -> uint8);
+// the host tabulates it with the reference's own expression for e = 0..cap and the kernel only
+// indexes lut[min(e,cap)], which makes the planes bit-exact by construction.
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+namespace {
+
+constexpr int kSpecBlocks = 1184;     // fixed: the per-block partial layout must not depend on the device
+constexpr int kSpecThreads = 256;
+
+struct SpecArgs {
+  const void* ref;
+  const void* tst;
+  const uint8_t* plane;
+  int64_t bands, npix;
+  int64_t sb, sp;             // element strides: band, pixel
+  uint16_t* errmax;
+  const uint8_t* lut_g; int cap_g; uint8_t* err8_g; int64_t* hist8_g;
+  const uint8_t* lut_z; int cap_z; uint8_t* err8_z; int64_t* hist8_z;
+  int want_sam, want_sid;
+  double* out;
+};
+
+template <typename T>
+__device__ __forceinline__ int ld(const T* p, int64_t i) { return (int)__ldg(p + i); }
+
+// thread per pixel; bands at stride sb (BSQ: coalesced across the warp for every band)
+template <typename T>
+__global__ void __launch_bounds__(kSpecThreads)
+spectral_pixel(SpecArgs g) {
+  __shared__ unsigned hg[256], hz[256];
+  __shared__ double red[3][kSpecThreads / 32];
+  const T* ref = static_cast<const T*>(g.ref);
+  const T* tst = static_cast<const T*>(g.tst);
+  const int tid = threadIdx.x;
+  hg[tid] = 0; hz[tid] = 0;
+  __syncthreads();
+  const int B = (int)g.bands;
+  double s_acos = 0.0, s_sid = 0.0, s_n = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * kSpecThreads + tid; p < g.npix; p += (int64_t)gridDim.x * kSpecThreads) {
+    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
+    long long dot = 0, na2 = 0, nr2 = 0, sa = 0, sr = 0;
+    int emax = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
+    const int64_t base = p * g.sp;
+    for (int b = 0; b < B; ++b) {
+      const int a = ld(ref, base + b * g.sb), r = ld(tst, base + b * g.sb);
+      emax = max(emax, abs(a - r));
+      dot += (long long)a * r; na2 += (long long)a * a; nr2 += (long long)r * r;
+      sa += a; sr += r; amin = min(amin, a); rmin = min(rmin, r);
+    }
+    if (!(v & DM_VALID_QUICKLOOK)) emax = 0;                  // quicklooks.py:134
+    if (g.errmax) g.errmax[p] = (uint16_t)emax;
+    if (g.err8_g) {
+      const uint8_t e8 = __ldg(g.lut_g + min(emax, g.cap_g));
+      g.err8_g[p] = e8;
+      if (g.hist8_g) atomicAdd(&hg[e8], 1u);
+    }
+    if (g.err8_z) {
+      const uint8_t e8 = __ldg(g.lut_z + min(emax, g.cap_z));
+      g.err8_z[p] = e8;
+      if (g.hist8_z) atomicAdd(&hz[e8], 1u);
+    }
+    if ((g.want_sam || g.want_sid) && (v & DM_VALID_SPECTRAL)) {
+      s_n += 1.0;
+      if (g.want_sam) {
+        const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
+        const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
+        double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
+        c = fmin(1.0, fmax(-1.0, c));
+        s_acos += acos(c);
+      }
+      if (g.want_sid) {
+        // Ap = (a - amin + 1e-12) / sum_b(a - amin + 1e-12); the integer part of the sum is exact
+        const double SA = (double)(sa - (long long)B * amin) + (double)B * 1e-12;
+        const double SR = (double)(sr - (long long)B * rmin) + (double)B * 1e-12;
+        double t = 0.0;
+        for (int b = 0; b < B; ++b) {
+          const int a = ld(ref, base + b * g.sb), r = ld(tst, base + b * g.sb);
+          const double ap = ((double)(a - amin) + 1e-12) / SA;
+          const double rp = ((double)(r - rmin) + 1e-12) / SR;
+          t += ap * log((ap + 1e-15) / (rp + 1e-15)) + rp * log((rp + 1e-15) / (ap + 1e-15));
+        }
+        s_sid += t;
+      }
+    }
+  }
+  // deterministic block reduction of the float partials
+  const int lane = tid & 31, warp = tid >> 5;
+  s_acos = warp_sum_f64(s_acos); s_sid = warp_sum_f64(s_sid); s_n = warp_sum_f64(s_n);
+  if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
+  __syncthreads();
+  if (tid == 0 && g.out) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    g.out[3 * blockIdx.x + 0] = t0; g.out[3 * blockIdx.x + 1] = t1; g.out[3 * blockIdx.x + 2] = t2;
+  }
+  if (g.hist8_g && hg[tid]) atomic_add_i64(g.hist8_g + tid, hg[tid]);
+  if (g.hist8_z && hz[tid]) atomic_add_i64(g.hist8_z + tid, hz[tid]);
+}
+
+// BIP: one warp per pixel; lanes stride over the contiguous spectrum (coalesced), shuffles combine.
+template <typename T>
+__global__ void __launch_bounds__(kSpecThreads)
+spectral_warp_bip(SpecArgs g) {
+  __shared__ unsigned hg[256], hz[256];
+  __shared__ double red[3][kSpecThreads / 32];
+  const T* ref = static_cast<const T*>(g.ref);
+  const T* tst = static_cast<const T*>(g.tst);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  hg[tid] = 0; hz[tid] = 0;
+  __syncthreads();
+  const int B = (int)g.bands;
+  double s_acos = 0.0, s_sid = 0.0, s_n = 0.0;     // meaningful in lane 0
+  const int64_t wstride = (int64_t)gridDim.x * (kSpecThreads / 32);
+  for (int64_t p = (int64_t)blockIdx.x * (kSpecThreads / 32) + warp; p < g.npix; p += wstride) {
+    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
+    long long dot = 0, na2 = 0, nr2 = 0, sa = 0, sr = 0;
+    int emax = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
+    const int64_t base = p * (int64_t)B;
+    for (int b = lane; b < B; b += 32) {
+      const int a = ld(ref, base + b), r = ld(tst, base + b);
+      emax = max(emax, abs(a - r));
+      dot += (long long)a * r; na2 += (long long)a * a; nr2 += (long long)r * r;
+      sa += a; sr += r; amin = min(amin, a); rmin = min(rmin, r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+      amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+      rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    }
+    const bool spec = (g.want_sam || g.want_sid) && (v & DM_VALID_SPECTRAL);
+    if (spec) {
+      dot = warp_sum_ll(dot); na2 = warp_sum_ll(na2); nr2 = warp_sum_ll(nr2);
+      sa = warp_sum_ll(sa); sr = warp_sum_ll(sr);
+    }
+    if (!(v & DM_VALID_QUICKLOOK)) emax = 0;
+    if (lane == 0) {
+      if (g.errmax) g.errmax[p] = (uint16_t)emax;
+      if (g.err8_g) {
+        const uint8_t e8 = __ldg(g.lut_g + min(emax, g.cap_g));
+        g.err8_g[p] = e8;
+        if (g.hist8_g) atomicAdd(&hg[e8], 1u);
+      }
+      if (g.err8_z) {
+        const uint8_t e8 = __ldg(g.lut_z + min(emax, g.cap_z));
+        g.err8_z[p] = e8;
+        if (g.hist8_z) atomicAdd(&hz[e8], 1u);
+      }
+    }
+    if (spec) {
+      if (lane == 0) {
+        s_n += 1.0;
+        if (g.want_sam) {
+          const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
+          const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
+          double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
+          c = fmin(1.0, fmax(-1.0, c));
+          s_acos += acos(c);
+        }
+      }
+      if (g.want_sid) {
+        const double SA = (double)(sa - (long long)B * amin) + (double)B * 1e-12;
+        const double SR = (double)(sr - (long long)B * rmin) + (double)B * 1e-12;
+        double t = 0.0;
+        for (int b = lane; b < B; b += 32) {
+          const int a = ld(ref, base + b), r = ld(tst, base + b);
+          const double ap = ((double)(a - amin) + 1e-12) / SA;
+          const double rp = ((double)(r - rmin) + 1e-12) / SR;
+          t += ap * log((ap + 1e-15) / (rp + 1e-15)) + rp * log((rp + 1e-15) / (ap + 1e-15));
+        }
+        t = warp_sum_f64(t);
+        if (lane == 0) s_sid += t;
+      }
+    }
+  }
+  if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
+  __syncthreads();
+  if (tid == 0 && g.out) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    g.out[3 * blockIdx.x + 0] = t0; g.out[3 * blockIdx.x + 1] = t1; g.out[3 * blockIdx.x + 2] = t2;
+  }
+  if (g.hist8_g && hg[tid]) atomic_add_i64(g.hist8_g + tid, hg[tid]);
+  if (g.hist8_z && hz[tid]) atomic_add_i64(g.hist8_z + tid, hz[tid]);
+}
+
+template <typename T>
+int run_spectral(const SpecArgs& g, bool bip, cudaStream_t s) {
+  if (bip && g.bands >= 16)
+    spectral_warp_bip<T><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);
+  else
+    spectral_pixel<T><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);
+  DM_LAUNCH_CHECK("spectral");
+  return DM_OK;
+}
+
+}  // namespace
+
+int spectral_nblocks() { return kSpecBlocks; }
+
+int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_out, const uint8_t* lut_g,
+                    int cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z, int cap_z,
+                    uint8_t* err8_z, int64_t* hist8_z, int want_sam, int want_sid, double* spectral_out,
+                    cudaStream_t s) {
+  if (!p.ref || !p.tst) return fail(DM_EARG, "dm_spectral: null pointer");
+  if (p.bands <= 0 || p.rows < 0 || p.width < 0) return fail(DM_EARG, "dm_spectral: bad geometry");
+  if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_spectral: bad layout");
+  if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_spectral: bad global LUT");
+  if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_spectral: bad zoom LUT");
+  if ((want_sam || want_sid) && !spectral_out) return fail(DM_EARG, "dm_spectral: spectral_out is null");
+  SpecArgs g;
+  g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.bands = p.bands; g.npix = p.rows * p.width;
+  const bool bip = p.layout == DM_BIP;
+  g.sb = bip ? 1 : p.band_stride; g.sp = bip ? p.bands : 1;
+  g.errmax = errmax_out;
+  g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
+  g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
+  g.want_sam = want_sam; g.want_sid = want_sid; g.out = spectral_out;
+  switch (p.dtype) {
+    case DM_U8: return run_spectral<uint8_t>(g, bip, s);
+    case DM_U16: return run_spectral<uint16_t>(g, bip, s);
+    case DM_I16: return run_spectral<int16_t>(g, bip, s);
+  }
+  return fail(DM_EARG, "dm_spectral: bad dtype");
+}
+
+}  // namespace dm

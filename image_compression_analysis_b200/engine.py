@@ -1,0 +1,379 @@
+"""Device-side evaluation of one original/decoded pair: buffers, kernel launches, combine.
+
+torch is plumbing here (device memory, streams, torch.distributed); every number comes from
+libdm_b200.so.  One `Partials` object holds all outputs of a pair in THREE flat device vectors so
+that multi-GPU combination is three allreduces and the host read-back is one copy:
+
+    isum  int64   [ sums B*8 | hist B*K | counts 3 | hist8_g 256 | hist8_z 256 ]      (SUM)
+    imax  int64   [ maxs B*8 ]                                                         (MAX)
+    fsum  float64 [ sum_acos, sum_sid, n_spec | lmse B | ssimw_sum B | ssimw_cnt B ]   (SUM)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DM_BIP, DM_BSQ, DM_I16, DM_NSTAT, DM_U8, DM_U16, DM_VALID_METRICS, DM_VALID_QUICKLOOK,
+                   DM_VALID_SPECTRAL, DmPair, check, lib)
+
+_DTYPE_CODES = {"uint8": DM_U8, "uint16": DM_U16, "int16": DM_I16}
+_TORCH_STORE = {"uint8": torch.uint8, "uint16": torch.int16, "int16": torch.int16}   # bytes only
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("image_compression_analysis_b200 needs a CUDA device: the distortion metrics "
+                           "have no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def dtype_code(np_dtype) -> int:
+    name = np.dtype(np_dtype).name
+    if name not in _DTYPE_CODES:
+        raise TypeError(f"unsupported sample type {name}: the GPU path handles uint8, uint16 and int16")
+    return _DTYPE_CODES[name]
+
+
+def integral_nodata(nodata, np_dtype) -> Optional[int]:
+    """ds.nodata as an integer the samples can equal, else None (a value no sample can take
+    never matches `band != nodata`, run_codec.py:250-259)."""
+    if nodata is None:
+        return None
+    try:
+        f = float(nodata)
+    except (TypeError, ValueError):
+        return None
+    if not np.isfinite(f) or f != int(f):
+        return None
+    info = np.iinfo(np.dtype(np_dtype))
+    v = int(f)
+    return v if info.min <= v <= info.max else None
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(arr, device=None, non_blocking: bool = True) -> torch.Tensor:
+    """numpy array / torch CPU tensor -> device tensor of the same bytes (uint16 stored as int16)."""
+    device = device or require_cuda()
+    if isinstance(arr, torch.Tensor):
+        t = arr
+        if t.dtype == torch.uint16:
+            t = t.view(torch.int16)
+        return t.to(device, non_blocking=non_blocking) if t.device.type == "cpu" else t
+    a = np.ascontiguousarray(arr)
+    if a.dtype == np.uint16:
+        a = a.view(np.int16)
+    elif a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    t = torch.from_numpy(a)
+    return t.to(device, non_blocking=non_blocking)
+
+
+@dataclass
+class DevicePair:
+    """An original/decoded pair resident in HBM (or a row strip of one)."""
+    ref: torch.Tensor
+    tst: torch.Tensor
+    np_dtype: str                 # "uint8" | "uint16" | "int16"
+    layout: str                   # "bsq" (B,H,W) | "bip" (H,W,B)
+    bands: int
+    rows: int
+    width: int
+    ref_nodata: Optional[int] = None
+    tst_nodata: Optional[int] = None
+    img_row0: int = 0             # image row of buffer row 0 (row strips)
+    img_rows: Optional[int] = None
+    band_stride: Optional[int] = None
+
+    def __post_init__(self):
+        if self.img_rows is None:
+            self.img_rows = self.rows
+        if self.band_stride is None:
+            self.band_stride = self.rows * self.width
+
+    @property
+    def npix(self) -> int:
+        return self.rows * self.width
+
+    def c_pair(self) -> DmPair:
+        p = DmPair()
+        p.ref, p.tst = self.ref.data_ptr(), self.tst.data_ptr()
+        p.dtype = _DTYPE_CODES[self.np_dtype]
+        p.layout = DM_BSQ if self.layout == "bsq" else DM_BIP
+        p.bands, p.rows, p.width, p.band_stride = self.bands, self.rows, self.width, self.band_stride
+        p.ref_has_nodata = 0 if self.ref_nodata is None else 1
+        p.ref_nodata = 0 if self.ref_nodata is None else int(self.ref_nodata)
+        p.tst_has_nodata = 0 if self.tst_nodata is None else 1
+        p.tst_nodata = 0 if self.tst_nodata is None else int(self.tst_nodata)
+        return p
+
+    @staticmethod
+    def from_arrays(ref, tst, layout: str = "bsq", ref_nodata=None, tst_nodata=None, device=None) -> "DevicePair":
+        """Upload a host pair.  ref/tst: numpy arrays or torch CPU tensors, (B,H,W) for "bsq",
+        (H,W,B) for "bip"; shapes and dtypes must match (run_codec.py:243-244)."""
+        shape_r, shape_t = tuple(ref.shape), tuple(tst.shape)
+        assert shape_r == shape_t and len(shape_r) == 3, "Reference and test must match in size and band count."
+        name = _np_name(ref)
+        assert name == _np_name(tst), "Reference and test must have the same sample type."
+        dtype_code(name)
+        if layout == "bsq":
+            B, H, W = shape_r
+        elif layout == "bip":
+            H, W, B = shape_r
+        else:
+            raise ValueError(f"layout must be 'bsq' or 'bip', not {layout!r}")
+        return DevicePair(to_device(ref, device), to_device(tst, device), name, layout, B, H, W,
+                          integral_nodata(ref_nodata, name), integral_nodata(tst_nodata, name))
+
+    def as_bsq(self) -> "DevicePair":
+        """Same pair in (B,H,W) layout (device transpose through dm_bip_to_bsq when needed)."""
+        if self.layout == "bsq":
+            return self
+        eb = 1 if self.np_dtype == "uint8" else 2
+        outs = []
+        for t in (self.ref, self.tst):
+            o = torch.empty((self.bands, self.rows, self.width), dtype=t.dtype, device=t.device)
+            check(lib().dm_bip_to_bsq(_ptr(t), _ptr(o), eb, self.bands, self.rows, self.width, _stream_ptr()))
+            outs.append(o)
+        return DevicePair(outs[0], outs[1], self.np_dtype, "bsq", self.bands, self.rows, self.width,
+                          self.ref_nodata, self.tst_nodata, self.img_row0, self.img_rows)
+
+
+def _np_name(a) -> str:
+    if isinstance(a, torch.Tensor):
+        return {torch.uint8: "uint8", torch.int16: "int16", torch.uint16: "uint16"}.get(a.dtype, str(a.dtype))
+    return np.dtype(a.dtype).name
+
+
+@dataclass
+class Want:
+    """Which parts of the path to evaluate for a pair."""
+    stats: bool = True            # compute_metrics partials (+ data range scan)
+    moments: bool = True          # False: PSNR-only variant (no SSIM moments)
+    hist_bins: int = 0            # per-band |d| histogram bins (0 = off, power of two <= 1024)
+    errmax: bool = False          # uint16 plane of max_b |d|
+    err8_caps: Tuple[Optional[float], Optional[float]] = (None, None)   # (global cap, zoom cap)
+    sam: bool = False
+    sid: bool = False
+    lmse: bool = False
+    ssim_gauss: bool = False
+    generic_stats: bool = False   # force the scalar cross-check kernel
+
+
+@dataclass
+class Partials:
+    """Device-resident outputs of one pair (or one strip); see the module docstring."""
+    bands: int
+    hist_bins: int
+    isum: torch.Tensor
+    imax: torch.Tensor
+    fsum: torch.Tensor
+    planes: Dict[str, torch.Tensor] = field(default_factory=dict)   # errmax / err8_g / err8_z / valid
+    np_dtype: str = "uint16"
+    used_mask: bool = False
+
+    # layout helpers ------------------------------------------------------------------------
+    @staticmethod
+    def sizes(bands: int, hist_bins: int) -> Tuple[int, int, int]:
+        return bands * DM_NSTAT + bands * hist_bins + 3 + 512, bands * DM_NSTAT, 3 + 3 * bands
+
+    @staticmethod
+    def allocate(bands: int, hist_bins: int, device, np_dtype: str) -> "Partials":
+        ni, nm, nf = Partials.sizes(bands, hist_bins)
+        return Partials(bands, hist_bins, torch.zeros(ni, dtype=torch.int64, device=device),
+                        torch.zeros(nm, dtype=torch.int64, device=device),
+                        torch.zeros(nf, dtype=torch.float64, device=device), {}, np_dtype)
+
+    def _o(self):
+        B, K = self.bands, self.hist_bins
+        o_hist = B * DM_NSTAT
+        o_cnt = o_hist + B * K
+        return o_hist, o_cnt, o_cnt + 3, o_cnt + 3 + 256
+
+    @property
+    def sums(self): return self.isum[: self.bands * DM_NSTAT]
+    @property
+    def hist(self):
+        o_hist, o_cnt, _, _ = self._o()
+        return self.isum[o_hist:o_cnt]
+    @property
+    def counts(self):
+        _, o_cnt, o_g, _ = self._o()
+        return self.isum[o_cnt:o_g]
+    @property
+    def hist8_g(self):
+        _, _, o_g, o_z = self._o()
+        return self.isum[o_g:o_z]
+    @property
+    def hist8_z(self):
+        _, _, _, o_z = self._o()
+        return self.isum[o_z:o_z + 256]
+    @property
+    def spec(self): return self.fsum[0:3]
+    @property
+    def lmse(self): return self.fsum[3:3 + self.bands]
+    @property
+    def ssimw_sum(self): return self.fsum[3 + self.bands:3 + 2 * self.bands]
+    @property
+    def ssimw_cnt(self): return self.fsum[3 + 2 * self.bands:3 + 3 * self.bands]
+
+    def allreduce_(self, group=None) -> "Partials":
+        """Combine the partials of all ranks in place: int64 SUM, int64 MAX, float64 SUM.
+
+        The only exchange step of the path: payload B*(8+K+8+3)*8 bytes, latency
+        bound.  Works on NCCL (device tensors) and on gloo (CPU tensors, used by the CPU tests)."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return self
+        works = [dist.all_reduce(self.isum, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                 dist.all_reduce(self.imax, op=dist.ReduceOp.MAX, group=group, async_op=True),
+                 dist.all_reduce(self.fsum, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+        for w in works:
+            w.wait()
+        return self
+
+    def to_host(self) -> "HostPartials":
+        flat = torch.cat([self.isum, self.imax, self.fsum.view(torch.int64)]).cpu().numpy()
+        ni, nm = self.isum.numel(), self.imax.numel()
+        return HostPartials(self.bands, self.hist_bins, flat[:ni].copy(), flat[ni:ni + nm].copy(),
+                            flat[ni + nm:].view(np.float64).copy(), self.np_dtype, self.used_mask)
+
+
+@dataclass
+class HostPartials:
+    bands: int
+    hist_bins: int
+    isum: np.ndarray
+    imax: np.ndarray
+    fsum: np.ndarray
+    np_dtype: str = "uint16"
+    used_mask: bool = False
+
+    @property
+    def sums(self): return self.isum[: self.bands * DM_NSTAT].reshape(self.bands, DM_NSTAT)
+    @property
+    def maxs(self): return self.imax.reshape(self.bands, DM_NSTAT)
+    @property
+    def hist(self):
+        o = self.bands * DM_NSTAT
+        return self.isum[o:o + self.bands * self.hist_bins].reshape(self.bands, max(self.hist_bins, 0)) \
+            if self.hist_bins else None
+    @property
+    def counts(self):
+        o = self.bands * DM_NSTAT + self.bands * self.hist_bins
+        return self.isum[o:o + 3]
+    @property
+    def hist8_g(self):
+        o = self.bands * DM_NSTAT + self.bands * self.hist_bins + 3
+        return self.isum[o:o + 256]
+    @property
+    def hist8_z(self):
+        o = self.bands * DM_NSTAT + self.bands * self.hist_bins + 3 + 256
+        return self.isum[o:o + 256]
+    @property
+    def spec(self): return self.fsum[0:3]
+    @property
+    def lmse(self): return self.fsum[3:3 + self.bands]
+    @property
+    def ssimw_sum(self): return self.fsum[3 + self.bands:3 + 2 * self.bands]
+    @property
+    def ssimw_cnt(self): return self.fsum[3 + 2 * self.bands:3 + 3 * self.bands]
+
+
+_LUT_CACHE: Dict[Tuple[float, int], torch.Tensor] = {}
+
+
+def _lut_on_device(cap: float, device) -> torch.Tensor:
+    from .finish import err8_lut
+    key = (float(cap), device.index if device.index is not None else 0)
+    t = _LUT_CACHE.get(key)
+    if t is None:
+        t = torch.from_numpy(err8_lut(cap)).to(device)
+        _LUT_CACHE[key] = t
+    return t
+
+
+def needs_plane(pair: DevicePair, valid) -> bool:
+    return valid is not None or pair.ref_nodata is not None or pair.tst_nodata is not None
+
+
+def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
+             out: Optional[Partials] = None, rows: Optional[Tuple[int, int]] = None,
+             data_range: Optional[float] = None, metrics_mask: bool = True,
+             plane: Optional[torch.Tensor] = None) -> Partials:
+    """Launch the kernels `want` asks for on the current stream; nothing is synchronised.
+
+    valid     optional device uint8 plane (rows*width, nonzero = valid): the caller's `valid`
+    out       accumulate into existing partials (row strips of one image on one GPU)
+    rows      buffer rows [begin,end) this call COUNTS for the stencil kernels; the buffer may hold
+              halo rows around them (img_row0 / img_rows in `pair` place the buffer in the image)
+    metrics_mask  False: run the fused stats unmasked even if a plane exists (the reference's
+              all-False-mask fallback, run_codec.py:264)
+    plane     a validity plane already computed for this buffer (skips dm_validity)
+    """
+    L = lib()
+    dev = pair.ref.device
+    st = _stream_ptr()
+    P = out if out is not None else Partials.allocate(pair.bands, want.hist_bins, dev, pair.np_dtype)
+    cp = pair.c_pair()
+    if plane is None and needs_plane(pair, valid):
+        plane = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+        check(L.dm_validity(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), st))
+        P.planes["valid"] = plane
+    if want.stats:
+        use = plane if (plane is not None and metrics_mask) else None
+        flags = (0 if want.moments else _lib.DM_STATS_NO_MOMENTS) | (_lib.DM_STATS_GENERIC if want.generic_stats else 0)
+        check(L.dm_fused_stats(C.byref(cp), _ptr(use), DM_VALID_METRICS, want.hist_bins, flags,
+                               _ptr(P.sums), _ptr(P.imax), _ptr(P.hist) if want.hist_bins else None, st))
+        P.used_mask = use is not None
+    cap_g, cap_z = want.err8_caps
+    if want.errmax or cap_g is not None or cap_z is not None or want.sam or want.sid:
+        nb = L.dm_spectral_nblocks()
+        spec_blocks = torch.empty(3 * nb, dtype=torch.float64, device=dev) if (want.sam or want.sid) else None
+        if want.errmax:
+            P.planes["errmax"] = torch.empty(pair.npix, dtype=torch.int16, device=dev)
+        lut_g = lut_z = None
+        if cap_g is not None:
+            lut_g = _lut_on_device(cap_g, dev)
+            P.planes["err8_g"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+        if cap_z is not None:
+            lut_z = _lut_on_device(cap_z, dev)
+            P.planes["err8_z"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+        check(L.dm_spectral(C.byref(cp), _ptr(plane), _ptr(P.planes.get("errmax")),
+                            _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(P.planes.get("err8_g")),
+                            _ptr(P.hist8_g),
+                            _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(P.planes.get("err8_z")),
+                            _ptr(P.hist8_z),
+                            1 if want.sam else 0, 1 if want.sid else 0, _ptr(spec_blocks), st))
+        if spec_blocks is not None:
+            P.spec.add_(spec_blocks.view(nb, 3).sum(dim=0))
+    if want.lmse or want.ssim_gauss:
+        bsq = pair.as_bsq()
+        cb = bsq.c_pair()
+        r0, r1 = rows if rows is not None else (0, pair.rows)
+        if want.lmse:
+            nb = L.dm_sobel_nblocks()
+            buf = torch.empty(pair.bands * nb, dtype=torch.float64, device=dev)
+            check(L.dm_sobel_lmse(C.byref(cb), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st))
+            P.lmse.add_(buf.view(pair.bands, nb).sum(dim=1))
+        if want.ssim_gauss:
+            if data_range is None:
+                raise ValueError("ssim_gauss needs data_range (the peak L of the SSIM constants)")
+            nb = L.dm_ssim_nblocks()
+            buf = torch.empty(pair.bands * nb * 2, dtype=torch.float64, device=dev)
+            check(L.dm_ssim_gauss(C.byref(cb), float(data_range), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st))
+            v = buf.view(pair.bands, nb, 2).sum(dim=1)
+            P.ssimw_sum.add_(v[:, 0])
+            P.ssimw_cnt.add_(v[:, 1])
+    return P

@@ -1,0 +1,163 @@
+/*
+ * dm_b200.h -- C ABI of libdm_b200.so: B200 (sm_100a) reconstruction-distortion kernels.
+ *
+ * This is the drop-in boundary for the one hot path of Angela0110/Image-compression-analysis:
+ * the metric evaluation tools/run_codec.py runs after every codec decode.  The reference is
+ * pure Python/numpy and has no FFI of its own; each entry point below names the reference
+ * function (file:line under /root/reference) whose ARITHMETIC it replaces.  The reference-side
+ * binding is ctypes; the host mirror of the reference's Python signatures
+ * lives in image_compression_analysis_b200/metrics.py and quicklooks.py.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer owned by the caller unless the name says `host`;
+ *    the library allocates nothing persistent; `stream` is a cudaStream_t passed as void*
+ *    (0 = legacy default stream);
+ *  - every call is asynchronous on `stream`; integer outputs ACCUMULATE into caller-zeroed
+ *    buffers (sums add, maxima max), so row strips / band groups / GPUs compose exactly;
+ *  - return value: 0 = ok, otherwise a DM_E* code; dm_last_error() gives the text (thread-local);
+ *  - there is no CPU path: without a CUDA device every compute entry point fails with DM_ECUDA.
+ *
+ * Cube geometry (dm_pair_t): `layout` DM_BSQ = (bands, rows, width) with `band_stride` elements
+ * between bands (rows contiguous), DM_BIP = (rows, width, bands) contiguous.  `rows` is the number
+ * of image rows present in the buffer; stencil kernels additionally take the image row index of
+ * buffer row 0 and the full image height so that row strips with halos shard across GPUs.
+ */
+#ifndef DM_B200_H
+#define DM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ABI_VERSION 2
+
+/* status codes */
+enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
+
+/* sample types (the reference path sees uint8 / uint16 / int16: run_codec.py:89-113) */
+enum { DM_U8 = 0, DM_U16 = 1, DM_I16 = 2 };
+
+/* in-memory interleave */
+enum { DM_BSQ = 0, DM_BIP = 1 };
+
+/* bits of the per-pixel validity plane written by dm_validity() */
+enum {
+  DM_VALID_METRICS = 1,   /* run_codec.py:249-263  compute_metrics mask            */
+  DM_VALID_QUICKLOOK = 2, /* quicklooks.py:35-45,128-130  write_error_max8 mask   */
+  DM_VALID_SPECTRAL = 4   /* run_codec.py:314-319  compute_sam_sid_lmse_caseB mask */
+};
+
+/* per-band integer partials written by dm_fused_stats(): two int64 arrays of DM_NSTAT per band */
+enum { DM_NSTAT = 8 };
+/* sums[band*DM_NSTAT + k], combined across shards with SUM */
+enum { DM_S_N = 0, DM_S_X = 1, DM_S_Y = 2, DM_S_XX = 3, DM_S_YY = 4, DM_S_XY = 5, DM_S_ABS = 6, DM_S_SSE = 7 };
+/* maxs[band*DM_NSTAT + k], combined across shards with MAX.  MAXERR is per band; the others are
+ * cube-wide quantities that the kernels may report on any band (the host takes the max over bands). */
+enum {
+  DM_M_MAXERR = 0,  /* max |x-y| over selected pixels of this band          (run_codec.py:275-276) */
+  DM_M_ABSXY = 1,   /* max(np.abs(x), np.abs(y)) over selected pixels; int16 -32768 wraps (:285)   */
+  DM_M_UMAX = 2,    /* max(0, max x) over ALL pixels of the reference        (run_codec.py:97,108)  */
+  DM_M_UNEGMIN = 3, /* max(0, -min x) over ALL pixels of the reference       (run_codec.py:107)     */
+  DM_M_LOW4 = 4,    /* 1 if any reference sample has (x & 0xF) != 0          (run_codec.py:98)      */
+  DM_M_LOW2 = 5,    /* 1 if any reference sample has (x & 0x3) != 0          (run_codec.py:109)     */
+  DM_M_SPARE0 = 6,
+  DM_M_SPARE1 = 7
+};
+
+/* dm_fused_stats flags */
+enum {
+  DM_STATS_NO_MOMENTS = 1, /* PSNR-only variant: S_X,S_Y,S_XX,S_YY,S_XY untouched, S_SSE direct  */
+  DM_STATS_GENERIC = 2     /* force the scalar any-layout kernel (cross-check / A-B timing)     */
+};
+
+typedef struct dm_pair {
+  const void* ref;      /* original cube (device)                    */
+  const void* tst;      /* decoded cube (device), same geometry      */
+  int32_t dtype;        /* DM_U8 / DM_U16 / DM_I16                   */
+  int32_t layout;       /* DM_BSQ / DM_BIP                           */
+  int64_t bands;
+  int64_t rows;         /* rows present in the buffer                */
+  int64_t width;
+  int64_t band_stride;  /* DM_BSQ: elements between bands (>= rows*width); ignored for DM_BIP */
+  int32_t ref_has_nodata, ref_nodata;  /* integer nodata of the original (rasterio ds.nodata) */
+  int32_t tst_has_nodata, tst_nodata;
+} dm_pair_t;
+
+/* library / device ------------------------------------------------------------------------ */
+int dm_abi_version(void);
+const char* dm_last_error(void);
+/* number of SMs, or a negative DM_E* code when no CUDA device is usable */
+int dm_device_sm_count(void);
+
+/* masks -------------------------------------------------------------------------------------
+ * Per-pixel validity plane (uint8, rows*width), bit set = pixel selected:
+ *   DM_VALID_METRICS   = valid_in AND every band != nodata in BOTH cubes   (run_codec.py:249-263)
+ *   DM_VALID_QUICKLOOK = dataset masks AND band 1 != nodata in both cubes  (quicklooks.py:35-45)
+ *   DM_VALID_SPECTRAL  = valid_in if given, else the two dataset masks     (run_codec.py:314-319)
+ * where a dataset mask is rasterio's dataset_mask(): any band != nodata (all valid without nodata).
+ * valid_in (uint8, nonzero = valid) may be NULL.  counts_out (3 x int64, accumulated) receives
+ * the number of pixels with each bit set. */
+int dm_validity(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out,
+                int64_t* counts_out, void* stream);
+
+/* fused single-pass integer reduction ---------------------------------------------------------
+ * Replaces the arithmetic of compute_metrics' band loop (run_codec.py:268-285) and of
+ * effective_data_range (run_codec.py:86-117): reads both cubes once and ACCUMULATES, per band,
+ * sums[DM_NSTAT] (add) and maxs[DM_NSTAT] (max) as laid out above, plus, when hist_bins > 0,
+ * hist[band*hist_bins + min(|x-y|, hist_bins-1)] (add).  `plane` (NULL = all pixels) selects
+ * pixels whose byte has the single bit `plane_bit` set; DM_M_UMAX.. are always over all pixels.
+ * hist_bins must be 0 or a power of two <= 1024. */
+int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, int32_t hist_bins,
+                   uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, void* stream);
+
+/* per-pixel spectral pass --------------------------------------------------------------------
+ * One pass over the spectral axis of every pixel.  Replaces the arithmetic of
+ *   write_error_max8   quicklooks.py:123-150  (max_b |A-B|, invalid -> 0, float32 scaling -> uint8)
+ *   SAM / SID          run_codec.py:328-339
+ * Outputs (each may be NULL to skip):
+ *   errmax_out  uint16 plane of max_b|x-y| (0 where the QUICKLOOK bit is clear)
+ *   err8_g/err8_z  uint8 planes lut_g[min(e,cap_g)] / lut_z[min(e,cap_z)]; the LUTs (cap+1 bytes,
+ *               device) are built by the host with the reference's own float32 expression
+ *   hist8_g/hist8_z  256-bin int64 histograms of the uint8 planes (accumulated; give the
+ *               STATISTICS_MEAN / STATISTICS_STDDEV tags of quicklooks.py:175-184 exactly)
+ *   spectral_out  double[3*dm_spectral_nblocks()] per-block partials {sum arccos, sum sid, n}
+ *               over pixels with the SPECTRAL bit (all pixels when plane == NULL), block-ordered
+ *               so the host can reduce them deterministically.  Written, not accumulated.
+ * want_sid = 0 skips SID (its partial is 0). */
+int dm_spectral_nblocks(void);
+int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
+                uint16_t* errmax_out,
+                const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
+                int32_t want_sam, int32_t want_sid, double* spectral_out, void* stream);
+
+/* Sobel LMSE -----------------------------------------------------------------------------------
+ * Replaces sobel_mag + mse in the LMSE loop (run_codec.py:123-137, 341-346): for every band,
+ * sum over pixels of (|grad ref| - |grad tst|)^2 with the 3x3 Sobel pair and edge replication.
+ * Counts buffer rows [row_begin,row_end); buffer row 0 is image row img_row0 of img_rows, and the
+ * buffer must hold one halo row on each side that is not an image border.
+ * out: double[bands * dm_sobel_nblocks()] per-(band,block) partials (written, not accumulated). */
+int dm_sobel_nblocks(void);
+int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,
+                  int64_t img_rows, double* out, void* stream);
+
+/* Gaussian-window SSIM (addition) --------------------------------------------
+ * 11-tap separable Gaussian (sigma 1.5, truncate 3.5), float64, skimage semantics
+ * (use_sample_covariance=False), mean over the image cropped by 5 px.  DM_BSQ only.
+ * out: double[bands * 2 * dm_ssim_nblocks()] per-(band,block) partials {sum of S, count} over the
+ * pixels of buffer rows [row_begin,row_end) that lie inside the crop (written, not accumulated).
+ * The buffer must hold 5 halo rows on each side that is not an image border (borders reflect). */
+int dm_ssim_nblocks(void);
+int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
+                  int64_t img_row0, int64_t img_rows, double* out, void* stream);
+
+/* layout helper: (rows,width,bands) -> (bands,rows,width), same dtype (1 or 2 bytes/sample) */
+int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands, int64_t rows,
+                  int64_t width, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DM_B200_H */

@@ -1,0 +1,223 @@
+"""GPU parity: the CUDA path (through the public Python mirror and the C-ABI library) against
+(a) the reference-generated golden fixtures and (b) the numpy oracle on seeded inputs.
+
+Bars: integers bit-exact; PSNR bit-exact (host math.log10 on exact integers);
+SSIM / SAM / SID / LMSE / Gaussian SSIM within 1e-6 relative (abs floor 1e-12)."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import goldenio
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+
+
+def _close(g, w, rel=REL):
+    return goldenio.close(g, w, rel=rel)
+
+
+def _check_metrics(got, want, exact_psnr=True):
+    assert set(want) <= set(got)
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, (int, np.integer)):
+            assert isinstance(g, int) and g == int(w), (k, g, w)
+        elif k.startswith("psnr") and exact_psnr:
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+        else:
+            assert isinstance(g, float) and _close(g, w), (k, g, w)
+
+
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+@pytest.mark.parametrize("name", goldenio.names())
+def test_compute_metrics_golden(name, layout):
+    import image_compression_analysis_b200 as dm
+    c = goldenio.load(name)
+    ref, tst = c["ref"], c["tst"]
+    if layout == "bip":
+        ref, tst = np.ascontiguousarray(np.moveaxis(ref, 0, -1)), np.ascontiguousarray(np.moveaxis(tst, 0, -1))
+    got = dm.compute_metrics_arrays(ref, tst, c["valid"], ref_nodata=c["ref_nodata"], tst_nodata=c["tst_nodata"],
+                                    layout=layout)
+    assert set(got) == set(c["compute_metrics"])
+    _check_metrics(got, c["compute_metrics"])
+
+
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+@pytest.mark.parametrize("name", goldenio.names())
+def test_sam_sid_lmse_golden(name, layout):
+    import image_compression_analysis_b200 as dm
+    c = goldenio.load(name)
+    ref, tst = c["ref"], c["tst"]
+    if layout == "bip":
+        ref, tst = np.ascontiguousarray(np.moveaxis(ref, 0, -1)), np.ascontiguousarray(np.moveaxis(tst, 0, -1))
+    got = dm.compute_sam_sid_lmse_caseB_arrays(ref, tst, c["valid"], ref_nodata=c["ref_nodata"],
+                                               tst_nodata=c["tst_nodata"], layout=layout)
+    assert set(got) == {"sam_deg", "sid", "lmse"}
+    for k, w in c["sam_sid_lmse"].items():
+        assert _close(got[k], w), (k, got[k], w)
+
+
+@pytest.mark.parametrize("name", goldenio.names())
+def test_error_max8_golden(name):
+    from image_compression_analysis_b200 import quicklooks as ql
+    c = goldenio.load(name)
+    for n, e in enumerate(c["err8"]):
+        got = ql.error_max8_arrays(c["ref"], c["tst"], e["cap_g"], e["cap_z"], a_nodata=c["ref_nodata"],
+                                   b_nodata=c["tst_nodata"])
+        assert np.array_equal(got["err8_g"], c["planes"][f"err8_{n}_g"])
+        assert np.array_equal(got["valid"].astype(np.uint8), c["planes"][f"err8_{n}_mask"])
+        assert e["name_g"] == f"recon_ERR8_0_{got['cap_g']}.tif"
+        assert float(e["tags_g"]["STATISTICS_MEAN"]) == got["mean_g"]
+        assert _close(got["std_g"], float(e["tags_g"]["STATISTICS_STDDEV"]), rel=1e-12)
+        if e["cap_z"] is not None:
+            assert np.array_equal(got["err8_z"], c["planes"][f"err8_{n}_z"])
+            assert e["name_z"] == f"recon_ERR8_0_{got['cap_z']}.tif"
+            assert float(e["tags_z"]["STATISTICS_MEAN"]) == got["mean_z"]
+
+
+def _rand_pair(seed, dtype, B, H, W, amp, lowbits=0):
+    rng = np.random.default_rng(seed)
+    info = np.iinfo(dtype)
+    ref = rng.integers(info.min, int(info.max) + 1, size=(B, H, W)).astype(dtype)
+    if lowbits:
+        ref = ((ref >> lowbits) << lowbits).astype(dtype)
+    dec = np.clip(ref.astype(np.int64) + rng.integers(-amp, amp + 1, size=ref.shape), info.min, info.max).astype(dtype)
+    return ref, dec
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+@pytest.mark.parametrize("dtype,B,H,W,amp,masked", [
+    ("uint16", 4, 257, 515, 40, False),      # odd sizes: scalar head/tail of the packed kernel
+    ("uint16", 4, 256, 512, 65535, True),    # full-range errors: every 32-bit partial at its bound
+    ("int16", 6, 130, 259, 3000, True),
+    ("int16", 12, 64, 100, 65535, False),
+    ("uint8", 3, 99, 131, 9, True),
+    ("uint16", 7, 67, 93, 500, True),        # odd band count (BIP -> generic kernel)
+    ("uint16", 180, 32, 48, 5, False),       # EnMAP band count
+])
+def test_fused_stats_vs_oracle(dtype, B, H, W, amp, masked, layout, generic):
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200.engine import DevicePair, Want, dtype_code
+    from image_compression_analysis_b200.metrics import _valid_to_device, metrics_partials
+    from oracle import distortion_oracle as orc
+    ref, dec = _rand_pair(7, dtype, B, H, W, amp)
+    valid = (np.random.default_rng(8).random((H, W)) < 0.7) if masked else None
+    want = orc.compute_metrics(ref, dec, valid, hist_bins=256, extras=True)
+    r, d = (ref, dec) if layout == "bsq" else (np.ascontiguousarray(np.moveaxis(ref, 0, -1)),
+                                                np.ascontiguousarray(np.moveaxis(dec, 0, -1)))
+    pair = DevicePair.from_arrays(r, d, layout)
+    P = metrics_partials(pair, _valid_to_device(valid, H, W, "shape"), Want(stats=True, hist_bins=256, generic_stats=generic))
+    h = P.to_host()
+    got = finish.finish_compute_metrics(dtype_code(dtype), h.sums, h.maxs, h.hist, extras=True)
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, np.ndarray):
+            assert np.array_equal(g, w), k
+        elif isinstance(w, (int, np.integer)):
+            assert g == int(w), (k, g, w)
+        elif k.startswith("psnr") or k.startswith("mae"):
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+        else:
+            assert _close(g, w, rel=1e-9), (k, g, w)
+
+
+@pytest.mark.parametrize("dtype", ["uint16", "int16"])
+def test_no_moments_variant_matches(dtype):
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    ref, dec = _rand_pair(21, dtype, 5, 200, 333, 65535)
+    pair = DevicePair.from_arrays(ref, dec)
+    a = evaluate(pair, Want(stats=True)).to_host()
+    b = evaluate(pair, Want(stats=True, moments=False)).to_host()
+    for k in (0, 6, 7):       # N, S|d|, SSE
+        assert np.array_equal(a.sums[:, k], b.sums[:, k])
+    assert np.array_equal(a.maxs, b.maxs)
+    d = dec.astype(np.int64) - ref.astype(np.int64)
+    assert np.array_equal(a.sums[:, 7], (d * d).reshape(5, -1).sum(1))
+
+
+def test_misaligned_views():
+    """Row strips of a cube whose row pitch is not a multiple of 16 bytes: the packed kernel must
+    peel a scalar head per band and still agree with numpy."""
+    import torch
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    ref, dec = _rand_pair(31, "uint16", 3, 41, 37, 300)
+    full = DevicePair.from_arrays(ref, dec)
+    for r0, r1 in [(1, 40), (3, 4), (0, 41), (7, 30)]:
+        # same storage, offset by r0 rows, band stride of the full cube
+        sub = DevicePair(full.ref.view(-1)[r0 * 37:], full.tst.view(-1)[r0 * 37:], "uint16", "bsq", 3, r1 - r0, 37,
+                         band_stride=41 * 37)
+        h = evaluate(sub, Want(stats=True)).to_host()
+        a = ref[:, r0:r1].astype(np.int64)
+        b = dec[:, r0:r1].astype(np.int64)
+        assert np.array_equal(h.sums[:, 7], ((a - b) ** 2).reshape(3, -1).sum(1))
+        assert np.array_equal(h.sums[:, 5], (a * b).reshape(3, -1).sum(1))
+        assert np.array_equal(h.maxs[:, 0], np.abs(a - b).reshape(3, -1).max(1))
+        assert int(h.sums[0, 0]) == (r1 - r0) * 37
+
+
+def test_ssim_gaussian_vs_oracle():
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import synth
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_a_pair(seed=3, bands=3, height=150, width=203, sigma=2.0)
+    want = orc.ssim_gaussian(ref, dec)
+    got = dm.ssim_gaussian_arrays(ref, dec)
+    assert set(got) == set(want)
+    for k in want:
+        assert _close(got[k], want[k]), (k, got[k], want[k])
+    # full-range noise (SSIM far from 1) and int16
+    ref, dec = _rand_pair(5, "int16", 2, 64, 80, 20000)
+    want = orc.ssim_gaussian(ref, dec, data_range=65535.0)
+    got = dm.ssim_gaussian_arrays(ref, dec, data_range=65535.0)
+    for k in want:
+        assert _close(got[k], want[k]), (k, got[k], want[k])
+
+
+def test_scalar_helpers_match_oracle():
+    import image_compression_analysis_b200 as dm
+    from oracle import distortion_oracle as orc
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 65536, size=(33, 41)).astype(np.uint16)
+    b = rng.integers(0, 65536, size=(33, 41)).astype(np.uint16)
+    assert dm.mse(a, b) == orc.mse(a, b)
+    assert dm.psnr(a, b, 65535) == orc.psnr(a, b, 65535)
+    assert dm.psnr(a, a, 65535) == float("inf")
+    assert _close(dm.ssim_global(a, b, 4095), orc.ssim_global(a, b, 4095), rel=1e-12)
+    cube = np.stack([a, b])
+    assert dm.effective_data_range_arrays(cube) == orc.effective_data_range(cube) == 65535
+    assert dm.effective_data_range_arrays((cube >> 4) << 4) == 4095
+    with pytest.raises(TypeError):
+        dm.mse(a.astype(np.float64), b.astype(np.float64))
+
+
+def test_path_level_functions_with_rasterio_stub(tmp_path):
+    """compute_metrics / compute_sam_sid_lmse_caseB / write_error_max8 with the reference's own
+    signatures, reading through `rasterio` (here: the in-memory stub from oracle/)."""
+    from pathlib import Path
+    from oracle import rasterio_stub
+    rasterio_stub.install()
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import quicklooks as ql
+    c = goldenio.load("b_i16_nodata_masked")
+    rasterio_stub.clear()
+    rasterio_stub.register("/mem/ref.tif", c["ref"], nodata=c["ref_nodata"])
+    rasterio_stub.register("/mem/tst.tif", c["tst"], nodata=c["tst_nodata"])
+    got = dm.compute_metrics(Path("/mem/ref.tif"), Path("/mem/tst.tif"), valid=c["valid"])
+    _check_metrics(got, c["compute_metrics"])
+    got = dm.compute_sam_sid_lmse_caseB(Path("/mem/ref.tif"), Path("/mem/tst.tif"), valid=c["valid"])
+    for k, w in c["sam_sid_lmse"].items():
+        assert _close(got[k], w), k
+    with pytest.raises(ValueError):
+        dm.compute_metrics(Path("/mem/ref.tif"), Path("/mem/tst.tif"), valid=np.ones((3, 3), bool))
+    e = c["err8"][0]
+    og, oz = ql.write_error_max8("/mem/ref.tif", "/mem/tst.tif", "/mem/out/recon", err_max_global=e["cap_g"],
+                                 err_max_zoom=e["cap_z"])
+    assert Path(og).name == e["name_g"] and oz is None
+    w = rasterio_stub.fetch(og)
+    assert np.array_equal(w.data[0], c["planes"]["err8_0_g"])
+    assert np.array_equal(w.mask.astype(np.uint8), c["planes"]["err8_0_mask"])
+    assert w.tags["STATISTICS_MEAN"] == e["tags_g"]["STATISTICS_MEAN"]
