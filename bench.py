@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- distortion-metric throughput (GB/s of image-pair bytes) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one Case-B EnMAP
+cube pair, 1024 x 1024 x 180 uint16, BIP, per GPU; a step evaluates everything compute_metrics
+returns (per-band and global PSNR / SSIM / MAXAE, data-range scan) plus SAM.  With N GPUs the image
+is N x 1024 rows sharded by row strips (weak scaling: per-GPU work fixed) and the step ends with the
+allreduce of the integer / float64 partials, the path's only exchange.
+
+One JSON line on stdout (rank 0):
+  value      whole-job GB/s with the cubes resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the public API from pinned HOST buffers (H2D + D2H inside)
+  roofline   the dominant kernel against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the numpy port of the reference (oracle/) on a bounded sample, rank 0, N=1 only
+`--impl reference` times that CPU port with all host cores instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "distortion-metric throughput (original+decoded image-pair bytes)"
+UNIT = "GB/s"
+BANDS, ROWS, WIDTH = 180, 1024, 1024
+PAIR_BYTES = 2 * 2 * BANDS * ROWS * WIDTH            # 754 974 720: SURVEY.md 8d algorithmic bytes
+WORKLOAD = "Case B EnMAP 1024x1024x180 uint16 BIP cube pair per GPU: compute_metrics (per-band+global PSNR/SSIM/MAXAE) + SAM"
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (pynvml, in a thread, during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the numpy port of the reference (oracle/), the ONE place the bench executes oracle code
+# ------------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_sample(rows: int, seed: int):
+    key = (rows, seed)
+    if key not in _CPU_CACHE:
+        from image_compression_analysis_b200 import synth
+        _CPU_CACHE.clear()
+        _CPU_CACHE[key] = synth.case_b_pair(seed=seed, bands=BANDS, height=rows, width=WIDTH, amp=3, layout="bsq")
+    return _CPU_CACHE[key]
+
+
+def _cpu_work(args):
+    """One worker: compute_metrics + SAM of the reference (numpy port) on its own strip.  The strip
+    is generated once per process (first call) and is not part of the timed calls after that."""
+    rows, seed, reps = args
+    from oracle import distortion_oracle as orc
+    ref, dec = _cpu_sample(rows, seed)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.compute_metrics(ref, dec, extras=False)
+        orc.sam_caseB(ref, dec)
+    return time.perf_counter() - t0, reps * 2 * ref.nbytes
+
+
+def cpu_baseline_single(rows: int = 512, reps: int = 1):
+    """Scalar (1 core) run of the reference port on a `rows` x 1024 x 180 strip."""
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(k, "1")
+    _cpu_sample(rows, 2)
+    dt, nbytes = _cpu_work((rows, 2, reps))
+    return {"value": nbytes / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{reps} x ({rows} rows x {WIDTH} x {BANDS} bands) strip of the workload, oracle/distortion_oracle.py "
+                      f"compute_metrics + sam_caseB, single thread, {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (numpy port; the real
+    reference cannot travel to the GPU box) with every host core, one strip per process."""
+    import multiprocessing as mp
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"                     # numpy elementwise code is single-threaded; one process per core
+    workers = max(1, min(cores, 64))
+    rows = 16                                   # per worker per step: 16 x 1024 x 180 -> 11.8 MB per pair
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(workers) as pool:
+        for it in range(max(1, args.warmup) + args.steps):
+            res = pool.map(_cpu_work, [(rows, 100, 1) for _ in range(workers)], chunksize=1)
+            if it >= max(1, args.warmup):
+                # step time = the slowest worker's own metric time (its strip is cached per process,
+                # so synthetic-input generation never enters the number)
+                times.append((max(r[0] for r in res), sum(r[1] for r in res)))
+    tot_t = sum(t for t, _ in times)
+    tot_b = sum(b for _, b in times)
+    value = tot_b / tot_t / 1e9
+    sample = (f"per step {workers} processes x one ({rows} rows x {WIDTH} x {BANDS} bands) strip each of the workload; "
+              f"oracle/distortion_oracle.py compute_metrics + sam_caseB (numpy port of run_codec.py:240-332); "
+              f"step time = slowest worker")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_rows_per_worker": rows, "workers": workers},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def make_device_pairs(torch, n_pairs: int, seed: int):
+    """Synthetic EnMAP-like BIP pairs generated on the device (14-in-16 reference, +-3 DN decode)."""
+    from image_compression_analysis_b200.engine import DevicePair
+    pairs = []
+    for i in range(n_pairs):
+        g = torch.Generator(device="cuda").manual_seed(seed * 1000 + i)
+        ref = torch.randint(0, 2500, (ROWS, WIDTH, BANDS), device="cuda", dtype=torch.int16, generator=g) * 4
+        noise = torch.randint(-3, 4, (ROWS, WIDTH, BANDS), device="cuda", dtype=torch.int16, generator=g)
+        tst = (ref + noise).clamp_(0, 32767)
+        pairs.append(DevicePair(ref, tst, "uint16", "bip", BANDS, ROWS, WIDTH))
+    return pairs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from image_compression_analysis_b200 import _lib, finish
+    from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
+
+    world, rank, local = _env_int("WORLD_SIZE", 1), _env_int("RANK", 0), _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.gpus != world and rank == 0:
+        print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: reporting n_gpus={world}", file=sys.stderr)
+    L = _lib.lib()
+    want = Want(stats=True, sam=True)
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    n_pairs = 3                                   # 2.26 GB rotating, every pair 6x the 126 MB L2
+    pairs = make_device_pairs(torch, n_pairs, seed=rank + 1)
+    outs = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(n_pairs)]
+
+    def step(i):
+        P = outs[i % n_pairs]
+        P.isum.zero_(); P.imax.zero_(); P.fsum.zero_()
+        evaluate(pairs[i % n_pairs], want, out=P)
+        if world > 1:
+            P.allreduce_()
+        return P
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.dm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = L.dm_launch_count() - launches0
+    clocks = sampler.stop()
+
+    # per-kernel timing of the dominant kernel(s): same launches, events around each kernel
+    kern_ms = {"dm_fused_stats": [], "dm_spectral": []}
+    for i in range(args.steps):
+        P = outs[i % n_pairs]
+        P.isum.zero_(); P.imax.zero_(); P.fsum.zero_()
+        for name, w in (("dm_fused_stats", Want(stats=True)), ("dm_spectral", Want(stats=False, sam=True))):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            evaluate(pairs[i % n_pairs], w, out=P)
+            b.record()
+            b.synchronize()
+            kern_ms[name].append(a.elapsed_time(b))
+    barrier()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * PAIR_BYTES * args.steps / (ms_total * 1e-3) / 1e9
+
+    # sanity: the step's result must be a real metric dict (guards against timing a no-op)
+    h = step(0).to_host()
+    torch.cuda.synchronize()
+    res = finish.finish_compute_metrics(_lib.DM_U16, h.sums, h.maxs)
+    sam = finish.finish_spectral(float(h.spec[0]), float(h.spec[1]), float(h.spec[2]), None, 1)
+    assert int(h.sums[0, 0]) == world * ROWS * WIDTH and res["max_abs_err"] == 3 and 0 < sam["sam_deg"] < 1, (res, sam)
+
+    # ---- end-to-end arm: pinned host cubes -> public API -> metrics dict -------------------------
+    e2e = None
+    if not args.no_e2e:
+        import image_compression_analysis_b200 as dm
+        host = []
+        for i in range(2):
+            r = torch.empty((ROWS, WIDTH, BANDS), dtype=torch.int16).pin_memory()
+            d = torch.empty((ROWS, WIDTH, BANDS), dtype=torch.int16).pin_memory()
+            r.copy_(pairs[i].ref); d.copy_(pairs[i].tst)
+            host.append((r.view(torch.uint16), d.view(torch.uint16)))
+        torch.cuda.synchronize()
+
+        def e2e_step(i):
+            r, d = host[i % 2]
+            pair = DevicePair.from_arrays(r, d, "bip")
+            P = evaluate(pair, want)
+            if world > 1:
+                P.allreduce_()
+            hp = P.to_host()                      # device -> host read of the step's result
+            out = finish.finish_compute_metrics(_lib.DM_U16, hp.sums, hp.maxs)
+            out.update(finish.finish_spectral(float(hp.spec[0]), float(hp.spec[1]), float(hp.spec[2]), None, 1))
+            return out, hp
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(e2e_steps):
+            out, hp = e2e_step(i)
+        b.record()
+        barrier()
+        ms_e2e = a.elapsed_time(b)
+        te = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item())
+        d2h = (hp.isum.nbytes + hp.imax.nbytes + hp.fsum.nbytes)
+        e2e = {"value": world * PAIR_BYTES * e2e_steps / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": PAIR_BYTES, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": ms_e2e / e2e_steps,
+               "api": "engine.DevicePair.from_arrays(pinned host cubes) -> evaluate -> Partials.to_host -> finish.*"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    stats_ms = sum(kern_ms["dm_fused_stats"]) / len(kern_ms["dm_fused_stats"])
+    spec_ms = sum(kern_ms["dm_spectral"]) / len(kern_ms["dm_spectral"])
+    dominant = "dm_spectral" if spec_ms >= stats_ms else "dm_fused_stats"
+    dom_ms = max(spec_ms, stats_ms)
+    achieved = PAIR_BYTES / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tr = ROOT / "profiles" / "traffic.json"
+    if tr.exists():
+        try:
+            traffic = json.loads(tr.read_text()).get(dominant)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "layout": "bip", "bands": BANDS, "rows_per_gpu": ROWS, "width": WIDTH,
+                   "pair_bytes_per_gpu": PAIR_BYTES, "l2_policy": f"inputs larger than L2: {n_pairs} distinct 755 MB pairs rotated",
+                   "sharding": "row strips, one per GPU; allreduce of integer/float64 partials ends the step" if world > 1 else "single GPU",
+                   "kernels_per_step": ["dm_fused_stats (stats_bip_packed)", "dm_spectral (SAM)"]},
+        "frac_of_hbm_peak": value / (world * peak),
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": UNIT,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": PAIR_BYTES,
+                     "launch_ms": {"dm_fused_stats": stats_ms, "dm_spectral": spec_ms}},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(rows=64, reps=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

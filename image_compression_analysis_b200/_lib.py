@@ -46,6 +46,7 @@ SYMBOLS = {
     "dm_abi_version": (C.c_int, []),
     "dm_last_error": (C.c_char_p, []),
     "dm_device_sm_count": (C.c_int, []),
+    "dm_launch_count": (C.c_int64, []),
     "dm_validity": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P]),
     "dm_fused_stats": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
     "dm_spectral_nblocks": (C.c_int, []),

@@ -12,6 +12,7 @@ namespace dm {
 int fail(int code, const char* fmt, ...);           // records dm_last_error(), returns code
 int cuda_fail(cudaError_t e, const char* what);     // DM_ECUDA with the CUDA error text
 int sm_count();                                     // SMs of the current device (cached), <0 on error
+void count_launch();                                // one more kernel launched (dm_launch_count)
 
 #define DM_CUDA(expr)                                              \
   do {                                                             \
@@ -21,6 +22,7 @@ int sm_count();                                     // SMs of the current device
 
 #define DM_LAUNCH_CHECK(name)                                       \
   do {                                                              \
+    ::dm::count_launch();                                           \
     cudaError_t dm_e_ = cudaGetLastError();                         \
     if (dm_e_ != cudaSuccess) return ::dm::cuda_fail(dm_e_, name);  \
   } while (0)

@@ -1,4 +1,5 @@
 // libdm_b200.so: C-ABI entry points (include/dm_b200.h), error reporting and device queries.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -7,6 +8,9 @@
 namespace dm {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -44,6 +48,7 @@ extern "C" {
 int dm_abi_version(void) { return DM_ABI_VERSION; }
 const char* dm_last_error(void) { return g_err; }
 int dm_device_sm_count(void) { return sm_count(); }
+int64_t dm_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int dm_validity(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts_out,
                 void* stream) {

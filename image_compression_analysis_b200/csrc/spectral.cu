@@ -38,6 +38,14 @@ struct SpecArgs {
 template <typename T>
 __device__ __forceinline__ int ld(const T* p, int64_t i) { return (int)__ldg(p + i); }
 
+// warp-aggregated shared-memory histogram update: error maps are mostly a handful of values, so a
+// plain atomicAdd would serialise 32 lanes on one address
+__device__ __forceinline__ void hist_add(unsigned* h, unsigned bin) {
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+}
+
 // thread per pixel; bands at stride sb (BSQ: coalesced across the warp for every band)
 template <typename T>
 __global__ void __launch_bounds__(kSpecThreads)
@@ -67,12 +75,12 @@ spectral_pixel(SpecArgs g) {
     if (g.err8_g) {
       const uint8_t e8 = __ldg(g.lut_g + min(emax, g.cap_g));
       g.err8_g[p] = e8;
-      if (g.hist8_g) atomicAdd(&hg[e8], 1u);
+      if (g.hist8_g) hist_add(hg, e8);
     }
     if (g.err8_z) {
       const uint8_t e8 = __ldg(g.lut_z + min(emax, g.cap_z));
       g.err8_z[p] = e8;
-      if (g.hist8_z) atomicAdd(&hz[e8], 1u);
+      if (g.hist8_z) hist_add(hz, e8);
     }
     if ((g.want_sam || g.want_sid) && (v & DM_VALID_SPECTRAL)) {
       s_n += 1.0;
@@ -154,12 +162,12 @@ spectral_warp_bip(SpecArgs g) {
       if (g.err8_g) {
         const uint8_t e8 = __ldg(g.lut_g + min(emax, g.cap_g));
         g.err8_g[p] = e8;
-        if (g.hist8_g) atomicAdd(&hg[e8], 1u);
+        if (g.hist8_g) hist_add(hg, e8);
       }
       if (g.err8_z) {
         const uint8_t e8 = __ldg(g.lut_z + min(emax, g.cap_z));
         g.err8_z[p] = e8;
-        if (g.hist8_z) atomicAdd(&hz[e8], 1u);
+        if (g.hist8_z) hist_add(hz, e8);
       }
     }
     if (spec) {

@@ -68,6 +68,13 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
   asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
   return r;
 }
+// prmt.b32 in its generic form: selector nibble bit 3 replicates the sign of the selected byte
+// (__byte_perm only documents the low three bits of every nibble)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
 __device__ __forceinline__ int hmax2(uint32_t packed) {   // horizontal max of the two u16 halves
   return max((int)(packed & 0xffffu), (int)(packed >> 16));
 }
@@ -354,7 +361,7 @@ stats_bsq_packed(StatsArgs g, int64_t chunk_vecs, int64_t nchunk) {
             uint32_t m = 0;
             if (MASK) {
               const uint32_t mw = w < 2 ? mv[r].x : mv[r].y;
-              m = __byte_perm(mw, 0, (w & 1) ? 0xbbaa : 0x9988);   // sign-replicate two mask bytes
+              m = prmt(mw, 0u, (w & 1) ? 0xbbaau : 0x9988u);   // sign-replicate two mask bytes
             }
             const uint32_t d = word_op<DT, MASK, MOMENTS, true>(a, c, xw[r][w], yw[r][w], m);
             hist_word<HIST>(hist_sh, K, lane, d, m, MASK, true);

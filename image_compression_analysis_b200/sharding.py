@@ -1,0 +1,101 @@
+"""Row-strip sharding of one image across the GPUs of a box, and the combine step.
+
+Every metric of the path is a sum / max over independent pixels, so the only
+exchange is an allreduce of the flat partial vectors (`Partials.allreduce_`): int64 SUM, int64 MAX
+and float64 SUM, a few KB, latency bound on NVLink.  Stencil metrics (Sobel LMSE, Gaussian SSIM)
+need halo rows: 1 and 5 rows on every interior strip edge, replicated when the strips are cut.
+
+The functions here are pure host logic (testable on CPU with gloo) plus thin calls into engine.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+HALO_SOBEL = 1
+HALO_SSIM = 5
+
+
+@dataclass(frozen=True)
+class Strip:
+    """Rows [row0,row1) of the image are COUNTED by this rank; [buf0,buf1) are resident (with halo)."""
+    rank: int
+    row0: int
+    row1: int
+    buf0: int
+    buf1: int
+
+    @property
+    def rows(self) -> int:
+        return self.row1 - self.row0
+
+    @property
+    def count_range(self) -> Tuple[int, int]:
+        """Counted rows in buffer coordinates."""
+        return self.row0 - self.buf0, self.row1 - self.buf0
+
+
+def strips(img_rows: int, world: int, halo: int = 0, align: int = 1) -> List[Strip]:
+    """Cut img_rows into `world` contiguous strips, sizes differing by at most `align` rows.
+
+    align > 1 keeps every strip start a multiple of `align` rows (row pitches that are not a
+    multiple of 16 bytes then still give 16-byte aligned strips for the vector kernels)."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    units = (img_rows + align - 1) // align
+    out = []
+    for r in range(world):
+        u0, u1 = units * r // world, units * (r + 1) // world
+        row0, row1 = min(u0 * align, img_rows), min(u1 * align, img_rows)
+        buf0 = max(0, row0 - halo) if row1 > row0 else row0
+        buf1 = min(img_rows, row1 + halo) if row1 > row0 else row1
+        out.append(Strip(r, row0, row1, buf0, buf1))
+    return out
+
+
+def cut_bsq(cube: np.ndarray, s: Strip) -> np.ndarray:
+    """(B,H,W) -> the strip's resident rows, contiguous."""
+    return np.ascontiguousarray(cube[:, s.buf0:s.buf1, :])
+
+
+def cut_bip(cube: np.ndarray, s: Strip) -> np.ndarray:
+    """(H,W,B) -> the strip's resident rows (already contiguous)."""
+    return cube[s.buf0:s.buf1]
+
+
+def evaluate_strip(ref, tst, s: Strip, img_rows: int, layout: str, want, valid=None, *, ref_nodata=None,
+                   tst_nodata=None, data_range: Optional[float] = None, group=None, reduce: bool = True):
+    """Evaluate this rank's strip and (optionally) allreduce the partials.
+
+    ref/tst: the strip's RESIDENT rows (with halo) as host arrays; `valid`: the caller's mask for
+    the same rows or None.  Point-wise kernels see only the counted rows; stencil kernels see the
+    whole buffer and count [row0,row1)."""
+    import torch
+    from .engine import DevicePair, Partials, Want, evaluate, to_device
+    full = DevicePair.from_arrays(ref, tst, layout, ref_nodata, tst_nodata)
+    full.img_row0, full.img_rows = s.buf0, img_rows
+    c0, c1 = s.count_range
+    W, B = full.width, full.bands
+    # the counted rows as a view of the same device buffers
+    if layout == "bsq":
+        core = DevicePair(full.ref.view(-1)[c0 * W:], full.tst.view(-1)[c0 * W:], full.np_dtype, "bsq", B, c1 - c0, W,
+                          full.ref_nodata, full.tst_nodata, s.row0, img_rows, band_stride=full.rows * W)
+    else:
+        core = DevicePair(full.ref.view(-1)[c0 * W * B:], full.tst.view(-1)[c0 * W * B:], full.np_dtype, "bip", B,
+                          c1 - c0, W, full.ref_nodata, full.tst_nodata, s.row0, img_rows)
+    vdev = None
+    if valid is not None:
+        vdev = to_device(np.ascontiguousarray(np.asarray(valid)[c0:c1].astype(bool)).reshape(-1))
+    point = Want(stats=want.stats, moments=want.moments, hist_bins=want.hist_bins, errmax=want.errmax,
+                 err8_caps=want.err8_caps, sam=want.sam, sid=want.sid, generic_stats=want.generic_stats)
+    P = Partials.allocate(B, want.hist_bins, full.ref.device, full.np_dtype)
+    if c1 > c0:
+        evaluate(core, point, vdev, out=P)
+        if want.lmse or want.ssim_gauss:
+            evaluate(full, Want(stats=False, lmse=want.lmse, ssim_gauss=want.ssim_gauss), out=P, rows=(c0, c1),
+                     data_range=data_range)
+    if reduce:
+        P.allreduce_(group)
+    return P

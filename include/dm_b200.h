@@ -90,6 +90,9 @@ int dm_abi_version(void);
 const char* dm_last_error(void);
 /* number of SMs, or a negative DM_E* code when no CUDA device is usable */
 int dm_device_sm_count(void);
+/* kernels this library has launched in this process so far (bench.py reports the difference over
+ * its timed region as "gpu_launches") */
+int64_t dm_launch_count(void);
 
 /* masks -------------------------------------------------------------------------------------
  * Per-pixel validity plane (uint8, rows*width), bit set = pixel selected:

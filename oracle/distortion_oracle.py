@@ -306,6 +306,27 @@ def compute_sam_sid_lmse_caseB(ref: np.ndarray, tst: np.ndarray, valid: Optional
     return {"sam_deg": sam_deg, "sid": sid, "lmse": float(acc / B)}
 
 
+def sam_caseB(ref: np.ndarray, tst: np.ndarray, valid: Optional[np.ndarray] = None) -> float:
+    """SAM part alone of compute_sam_sid_lmse_caseB (run_codec.py:312-332): the float64 casts,
+    the mask gather and the arccos mean exactly as the reference performs them, without the SID
+    and LMSE that the reference function always computes alongside.  bench.py's CPU arm uses it
+    when the GPU step it is compared with evaluates SAM only."""
+    B, H, W = ref.shape
+    A = ref.astype(np.float64)
+    R = tst.astype(np.float64)
+    vm = valid.astype(bool) if valid is not None else np.ones((H, W), bool)
+    sel = vm.ravel()
+    A2 = A.reshape(B, -1)[:, sel]
+    R2 = R.reshape(B, -1)[:, sel]
+    if A2.shape[1] == 0:
+        return float("nan")
+    dot = np.sum(A2 * R2, axis=0)
+    na = np.sqrt(np.sum(A2 * A2, axis=0)) + 1e-12
+    nr = np.sqrt(np.sum(R2 * R2, axis=0)) + 1e-12
+    cosang = np.clip(dot / (na * nr), -1.0, 1.0)
+    return float(np.degrees(np.mean(np.arccos(cosang))))
+
+
 # --------------------------------------------------------------------------
 # error quicklooks (quicklooks.py:115-207) -- pixel content only, no file I/O
 # --------------------------------------------------------------------------
