@@ -423,10 +423,10 @@ __device__ __forceinline__ void load_cols(const uint32_t* p, uint32_t (&w)[C]) {
 }
 
 template <int DT, bool MASK, bool MOMENTS, bool HIST, int C>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(384)
 stats_bip_packed(StatsArgs g, BipGeom geo) {
   constexpr int NB = 2 * C;      // bands per thread
-  constexpr int U = 2;           // pixel-pair steps in flight
+  constexpr int U = 4;           // pixel-pair steps in flight
   extern __shared__ unsigned char smem_raw[];
   const int B = (int)g.bands, K = g.hist_bins;
   unsigned long long* sh_sums = reinterpret_cast<unsigned long long*>(smem_raw);   // [B][DM_NSTAT]
@@ -477,43 +477,51 @@ stats_bip_packed(StatsArgs g, BipGeom geo) {
   using FalseT = std::false_type;
 
   if (prow < geo.ppb) {
-    const int64_t gstride = gridDim.x;
-    for (int64_t gi = blockIdx.x; gi < geo.ngroups; gi += gstride * U) {
-      uint32_t xa[U][C], xb[U][C], ya[U][C], yb[U][C];
-      uint32_t m[U];
+    // running pointers: pixel A of this thread's first step; pixel B sits offb words further on, the
+    // next step of this block gstep words further on (64-bit adds instead of index arithmetic)
+    const int64_t offb = (int64_t)geo.ppb * geo.words;
+    const int64_t gstep = (int64_t)gridDim.x * 2 * offb;
+    const int64_t first = ((int64_t)blockIdx.x * 2 * geo.ppb + prow) * geo.words + col;
+    const uint32_t* pr = ref + first;
+    const uint32_t* pt = tst + first;
+    const uint8_t* pm = MASK ? g.plane + (int64_t)blockIdx.x * 2 * geo.ppb + prow : nullptr;
+    const int64_t mstep = (int64_t)gridDim.x * 2 * geo.ppb;
+    int64_t left = geo.ngroups > blockIdx.x ? (geo.ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // steps of this block
+    any = left > 0;
+    auto run = [&](auto ucount) {
+      constexpr int UU = decltype(ucount)::value;
+      uint32_t xa[UU][C], xb[UU][C], ya[UU][C], yb[UU][C];
+      uint32_t m[UU];
 #pragma unroll
-      for (int r = 0; r < U; ++r) {
-        const int64_t gg = gi + r * gstride;
-        if (gg < geo.ngroups) {
-          const int64_t pa = gg * 2 * geo.ppb + prow, pb = pa + geo.ppb;
-          load_cols<C>(ref + pa * geo.words + col, xa[r]);
-          load_cols<C>(ref + pb * geo.words + col, xb[r]);
-          load_cols<C>(tst + pa * geo.words + col, ya[r]);
-          load_cols<C>(tst + pb * geo.words + col, yb[r]);
-          if (MASK) {
-            const uint32_t sa = (g.plane[pa] & g.plane_bit) ? 0xffffu : 0u;
-            const uint32_t sb = (g.plane[pb] & g.plane_bit) ? 0xffff0000u : 0u;
-            m[r] = sa | sb;
-          }
+      for (int r = 0; r < UU; ++r) {
+        load_cols<C>(pr + r * gstep, xa[r]);
+        load_cols<C>(pr + r * gstep + offb, xb[r]);
+        load_cols<C>(pt + r * gstep, ya[r]);
+        load_cols<C>(pt + r * gstep + offb, yb[r]);
+        if (MASK) {
+          const uint32_t sa = (pm[r * mstep] & g.plane_bit) ? 0xffffu : 0u;
+          const uint32_t sb = (pm[r * mstep + geo.ppb] & g.plane_bit) ? 0xffff0000u : 0u;
+          m[r] = sa | sb;
         }
       }
 #pragma unroll
-      for (int r = 0; r < U; ++r) {
-        const int64_t gg = gi + r * gstride;
-        if (gg < geo.ngroups) {
-          step(xa[r], xb[r], ya[r], yb[r], MASK ? m[r] : 0xffffffffu, TrueT());
-          if (MASK) n += ((m[r] & 1u) ? 1 : 0) + ((m[r] >> 31) ? 1 : 0);
-          else n += 2;
-        }
+      for (int r = 0; r < UU; ++r) {
+        step(xa[r], xb[r], ya[r], yb[r], MASK ? m[r] : 0xffffffffu, TrueT());
+        if (MASK) n += ((m[r] & 1u) ? 1 : 0) + ((m[r] >> 31) ? 1 : 0);
+        else n += 2;
       }
-      any = true;
-      since_spill += U;
-      if (since_spill >= 126) {
+      pr += UU * gstep; pt += UU * gstep;
+      if (MASK) pm += UU * mstep;
+      left -= UU;
+      since_spill += UU;
+      if (since_spill >= 128 - U) {
         since_spill = 0;
 #pragma unroll
         for (int j = 0; j < NB; ++j) a[j].spill();
       }
-    }
+    };
+    while (left >= U) run(std::integral_constant<int, U>());
+    while (left > 0) run(std::integral_constant<int, 1>());
     // leftover pixels (< 2*ppb), one at a time, by block 0
     if (blockIdx.x == 0) {
       const int64_t p0 = geo.ngroups * 2 * geo.ppb;
@@ -773,7 +781,7 @@ int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, 
     packed = p.dtype != DM_U8 && (B % 2 == 0) && (ra % 4 == 0) && (ta % 4 == 0) && B <= 2048;
     if (packed) {
       bip_cols = (B % 4 == 0 && ra % 8 == 0 && ta % 8 == 0) ? 2 : 1;
-      if ((B / 2) / bip_cols > 512) packed = false;
+      if ((B / 2) / bip_cols > 384) packed = false;
       const size_t smem = (size_t)B * DM_NSTAT * 8 + (size_t)B * 4 + 32 + (size_t)hist_bins * B * 4;
       if (smem > 200 * 1024) packed = false;
     }

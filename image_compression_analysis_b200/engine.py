@@ -169,6 +169,7 @@ class Want:
     lmse: bool = False
     ssim_gauss: bool = False
     generic_stats: bool = False   # force the scalar cross-check kernel
+    fused: bool = True            # allow the one-pass BIP kernel (dm_fused_bip) when it applies
 
 
 @dataclass
@@ -331,33 +332,48 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
         plane = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
         check(L.dm_validity(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), st))
         P.planes["valid"] = plane
-    if want.stats:
-        use = plane if (plane is not None and metrics_mask) else None
-        flags = (0 if want.moments else _lib.DM_STATS_NO_MOMENTS) | (_lib.DM_STATS_GENERIC if want.generic_stats else 0)
-        check(L.dm_fused_stats(C.byref(cp), _ptr(use), DM_VALID_METRICS, want.hist_bins, flags,
-                               _ptr(P.sums), _ptr(P.imax), _ptr(P.hist) if want.hist_bins else None, st))
-        P.used_mask = use is not None
     cap_g, cap_z = want.err8_caps
-    if want.errmax or cap_g is not None or cap_z is not None or want.sam or want.sid:
+    want_planes = want.errmax or cap_g is not None or cap_z is not None
+    use = plane if (plane is not None and metrics_mask) else None
+    spec_blocks = None
+    lut_g = lut_z = None
+    if want_planes or want.sam or want.sid:
         nb = L.dm_spectral_nblocks()
-        spec_blocks = torch.empty(3 * nb, dtype=torch.float64, device=dev) if (want.sam or want.sid) else None
+        if want.sam or want.sid:
+            spec_blocks = torch.empty(3 * nb, dtype=torch.float64, device=dev)
         if want.errmax:
             P.planes["errmax"] = torch.empty(pair.npix, dtype=torch.int16, device=dev)
-        lut_g = lut_z = None
         if cap_g is not None:
             lut_g = _lut_on_device(cap_g, dev)
             P.planes["err8_g"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
         if cap_z is not None:
             lut_z = _lut_on_device(cap_z, dev)
             P.planes["err8_z"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
-        check(L.dm_spectral(C.byref(cp), _ptr(plane), _ptr(P.planes.get("errmax")),
-                            _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(P.planes.get("err8_g")),
-                            _ptr(P.hist8_g),
-                            _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(P.planes.get("err8_z")),
-                            _ptr(P.hist8_z),
+    spectral_args = (_ptr(P.planes.get("errmax")),
+                     _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(P.planes.get("err8_g")), _ptr(P.hist8_g),
+                     _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(P.planes.get("err8_z")), _ptr(P.hist8_z))
+    done_stats = done_spectral = False
+    # one-pass BIP kernel: stats + error planes + SAM from a single read (the plane selects METRICS
+    # pixels for the stats and QUICKLOOK / SPECTRAL pixels for the rest, so it needs use == plane)
+    if (want.stats and want.moments and not want.hist_bins and not want.generic_stats and not want.sid
+            and (want_planes or want.sam) and pair.layout == "bip" and use is plane and want.fused):
+        rc = L.dm_fused_bip(C.byref(cp), _ptr(plane), _ptr(P.sums), _ptr(P.imax), *spectral_args,
+                            1 if want.sam else 0, _ptr(spec_blocks), st)
+        if rc == _lib.DM_OK:
+            done_stats = done_spectral = True
+            P.used_mask = use is not None
+        elif rc != _lib.DM_EUNSUPPORTED:
+            check(rc)
+    if want.stats and not done_stats:
+        flags = (0 if want.moments else _lib.DM_STATS_NO_MOMENTS) | (_lib.DM_STATS_GENERIC if want.generic_stats else 0)
+        check(L.dm_fused_stats(C.byref(cp), _ptr(use), DM_VALID_METRICS, want.hist_bins, flags,
+                               _ptr(P.sums), _ptr(P.imax), _ptr(P.hist) if want.hist_bins else None, st))
+        P.used_mask = use is not None
+    if (want_planes or want.sam or want.sid) and not done_spectral:
+        check(L.dm_spectral(C.byref(cp), _ptr(plane), *spectral_args,
                             1 if want.sam else 0, 1 if want.sid else 0, _ptr(spec_blocks), st))
-        if spec_blocks is not None:
-            P.spec.add_(spec_blocks.view(nb, 3).sum(dim=0))
+    if spec_blocks is not None:
+        P.spec.add_(spec_blocks.view(-1, 3).sum(dim=0))
     if want.lmse or want.ssim_gauss:
         bsq = pair.as_bsq()
         cb = bsq.c_pair()

@@ -136,6 +136,18 @@ int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
                 const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
                 int32_t want_sam, int32_t want_sid, double* spectral_out, void* stream);
 
+/* one-pass BIP kernel: dm_fused_stats (moments, no histogram) + dm_spectral (error planes, SAM) from a
+ * SINGLE read of both cubes -- the tile is staged once in shared memory by TMA bulk copies and
+ * consumed by a per-band and a per-pixel warp group.  Same outputs and conventions as the two
+ * entry points above (spectral_out: double[3*dm_spectral_nblocks()], SID slot 0).  Supports DM_BIP,
+ * 16-bit samples, bands a multiple of 4 in 4..256, 16-byte aligned cubes; anything else returns
+ * DM_EUNSUPPORTED and the caller uses the two separate passes. */
+int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
+                 uint16_t* errmax_out,
+                 const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                 const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
+                 int32_t want_sam, double* spectral_out, void* stream);
+
 /* Sobel LMSE -----------------------------------------------------------------------------------
  * Replaces sobel_mag + mse in the LMSE loop (run_codec.py:123-137, 341-346): for every band,
  * sum over pixels of (|grad ref| - |grad tst|)^2 with the 3x3 Sobel pair and edge replication.

@@ -221,3 +221,82 @@ def test_path_level_functions_with_rasterio_stub(tmp_path):
     assert np.array_equal(w.data[0], c["planes"]["err8_0_g"])
     assert np.array_equal(w.mask.astype(np.uint8), c["planes"]["err8_0_mask"])
     assert w.tags["STATISTICS_MEAN"] == e["tags_g"]["STATISTICS_MEAN"]
+
+
+def _fused_vs_separate(ref_bsq, dec_bsq, valid, ref_nodata=None, tst_nodata=None, caps=(255, 32)):
+    """dm_fused_bip (one pass) against dm_fused_stats + dm_spectral (two passes) on the BIP view."""
+    import torch
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    from image_compression_analysis_b200.metrics import _valid_to_device
+    r = np.ascontiguousarray(np.moveaxis(ref_bsq, 0, -1))
+    d = np.ascontiguousarray(np.moveaxis(dec_bsq, 0, -1))
+    H, W, B = r.shape
+    pair = DevicePair.from_arrays(r, d, "bip", ref_nodata, tst_nodata)
+    vdev = _valid_to_device(valid, H, W, "shape")
+    outs = []
+    for fused in (True, False):
+        P = evaluate(pair, Want(stats=True, sam=True, errmax=True, err8_caps=caps, fused=fused), vdev)
+        torch.cuda.synchronize()
+        outs.append((P.to_host(), {k: v.cpu().numpy() for k, v in P.planes.items()}))
+    (hf, pf), (hs, ps) = outs
+    assert np.array_equal(hf.isum, hs.isum)
+    assert np.array_equal(hf.imax.reshape(-1, 8).max(0)[1:], hs.imax.reshape(-1, 8).max(0)[1:])   # cube-wide maxima
+    assert np.array_equal(hf.maxs[:, 0], hs.maxs[:, 0])                                           # per-band max|d|
+    for k in ("errmax", "err8_g", "err8_z"):
+        assert np.array_equal(pf[k], ps[k]), k
+    assert hf.spec[2] == hs.spec[2]
+    assert goldenio.close(hf.spec[0], hs.spec[0], rel=1e-12)
+    return hf
+
+
+@pytest.mark.parametrize("name", ["a_gauss", "a_identical", "a_near3_masked", "a_mask_all_false", "b_u16_masked",
+                                  "b_i16_nodata", "b_i16_nodata_masked", "b_zero_spectra"])
+def test_fused_bip_equals_two_pass_on_goldens(name):
+    from image_compression_analysis_b200 import _lib
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    c = goldenio.load(name)
+    assert c["ref"].shape[0] % 4 == 0
+    hf = _fused_vs_separate(c["ref"], c["tst"], c["valid"], c["ref_nodata"], c["tst_nodata"])
+    # and the fused kernel really ran (a second call must not return DM_EUNSUPPORTED)
+    import ctypes as C
+    import torch
+    r = np.ascontiguousarray(np.moveaxis(c["ref"], 0, -1))
+    pair = DevicePair.from_arrays(r, r, "bip")
+    sums = torch.zeros(pair.bands * 8, dtype=torch.int64, device="cuda")
+    maxs = torch.zeros_like(sums)
+    rc = _lib.lib().dm_fused_bip(C.byref(pair.c_pair()), None, sums.data_ptr(), maxs.data_ptr(), None, None, 0, None,
+                                 None, None, 0, None, None, 0, None, None)
+    assert rc == _lib.DM_OK, _lib.lib().dm_last_error()
+    assert int(sums[0].item()) == pair.npix
+
+
+@pytest.mark.parametrize("dtype,B,H,W,amp,masked", [
+    ("uint16", 180, 37, 53, 5, False),       # EnMAP bands, odd pixel count: generic tail tile + single pixel
+    ("uint16", 180, 64, 64, 65535, True),    # full-range errors, every partial at its bound
+    ("int16", 180, 40, 41, 30000, True),
+    ("uint16", 256, 16, 40, 65535, False),   # the largest band count the lo/hi partials allow
+    ("int16", 4, 129, 257, 700, False),
+    ("uint16", 8, 300, 301, 9, True),
+])
+def test_fused_bip_vs_oracle(dtype, B, H, W, amp, masked):
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200.engine import dtype_code
+    from oracle import distortion_oracle as orc
+    ref, dec = _rand_pair(11, dtype, B, H, W, amp)
+    if amp == 65535 and dtype == "uint16":
+        ref[:, :8] = 65535; dec[:, :8] = 0          # adversarial block: maximal products everywhere
+    valid = (np.random.default_rng(12).random((H, W)) < 0.6) if masked else None
+    hf = _fused_vs_separate(ref, dec, valid)
+    got = finish.finish_compute_metrics(dtype_code(dtype), hf.sums, hf.maxs)
+    want = orc.compute_metrics(ref, dec, valid, extras=False)
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, int):
+            assert g == w, (k, g, w)
+        elif k.startswith("psnr"):
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+        else:
+            assert _close(g, w, rel=1e-9), (k, g, w)
+    sam_want = orc.sam_caseB(ref, dec, valid)
+    sam_got = finish.finish_spectral(float(hf.spec[0]), 0.0, float(hf.spec[2]), None, H * W)["sam_deg"]
+    assert _close(sam_got, sam_want), (sam_got, sam_want)

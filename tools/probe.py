@@ -52,6 +52,8 @@ def main():
             "moments+hist256": Want(stats=True, hist_bins=256),
             "generic": Want(stats=True, generic_stats=True),
             "spectral sam": Want(stats=False, sam=True),
+            "stats+sam (fused if bip)": Want(stats=True, sam=True),
+            "stats+sam+err8 (fused if bip)": Want(stats=True, sam=True, err8_caps=(255, 32)),
             "spectral errmax+err8": Want(stats=False, err8_caps=(255, 32)),
         }
         if args.what == "all":
