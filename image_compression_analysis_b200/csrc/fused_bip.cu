@@ -8,16 +8,18 @@
 // staged ONCE in shared memory and consumed by two specialised warp groups at the same time:
 //
 //   warp 0            producer: one elected lane streams tiles of P pixels (both cubes) into a
-//                     2-stage shared-memory ring with cp.async.bulk (TMA, 1-D) + mbarrier tx counts;
+//                     4-stage shared-memory ring with cp.async.bulk (TMA, 1-D) + mbarrier tx counts,
+//                     so up to three tiles (138 KB) are in flight per SM while one is consumed;
 //   warps 1..6        "band" group: thread <-> 4 fixed bands (one 8-byte column pair), walks the
 //                     tile's pixels two at a time and pairs them band-wise with PRMT so that the
 //                     packed dp2a arithmetic of stats.cu applies; accumulators stay in registers
 //                     for the whole kernel;
 //   warps 7..10       "pixel" group: thread <-> pixel, walks the spectrum in natural (band-pair)
 //                     words: packed |d| max, dp2a dot / |a|^2 / |r|^2 as lo/hi 32-bit partials that
-//                     cannot overflow for B <= 256 bands, then float64 sqrt/div/acos per pixel.
+//                     cannot overflow for B <= 256 bands, then float64 sqrt/div/acos per pixel.  A tile
+//                     has 64 pixels, so the two halves of the group take alternate tiles.
 //
-// A stage is released (empty mbarrier) when every consumer warp has arrived.  The kernel is
+// A stage is released (empty mbarrier) when every consumer warp that reads it has arrived.  The kernel is
 // persistent: one CTA per SM, tiles strided over CTAs.  Shared-memory reads are conflict free for
 // EnMAP's 180 bands (pixel pitch 45 x 8 B, odd).  See DESIGN.md for the instruction budget.
 
@@ -32,8 +34,9 @@ namespace {
 constexpr int kBandWarps = 6, kPixelWarps = 4;
 constexpr int kBandThreads = kBandWarps * 32, kPixelThreads = kPixelWarps * 32;
 constexpr int kThreads = 32 + kBandThreads + kPixelThreads;     // 352
-constexpr int kStages = 2;
-constexpr int kStageBytesMax = 92160;                            // 2 cubes x 128 px x 180 bands x 2 B
+constexpr int kStages = 4;
+constexpr int kTilePixels = 64;                                  // pixels per tile (one half of the pixel group)
+constexpr int kStageBytesMax = 46080;                            // 2 cubes x 64 px x 180 bands x 2 B
 constexpr int kMaxSpecBlocks = 1184;                             // == dm_spectral_nblocks()
 
 struct FusedArgs {
@@ -105,11 +108,13 @@ struct BandAcc {
   }
 };
 
-// one packed word of one band (two pixels); x,y already in the unsigned domain and masked
-template <bool PAIR>
+// one packed word of one band (two pixels); x,y already in the unsigned domain and masked.
+// TRACK: also fold max(x,y) into maxsel_u (the masked / int16 variants; the plain uint16 variant
+// takes the maxima of the natural words instead, two words per VIMNMX3)
+template <bool PAIR, bool TRACK>
 __device__ __forceinline__ void band_word(BandAcc& a, uint32_t x, uint32_t y, uint32_t& maxsel_u) {
   const uint32_t mx = vmaxu2(x, y), mn = vminu2(x, y), d = mx - mn;
-  maxsel_u = vmaxu2(maxsel_u, mx);
+  if (TRACK) maxsel_u = vmaxu2(maxsel_u, mx);
   a.maxd = vmaxu2(a.maxd, d);
   const uint32_t ones = PAIR ? 0x0101u : 0x0001u;
   uint32_t px = __byte_perm(x, 0, 0x3120), py = __byte_perm(y, 0, 0x3120);
@@ -128,7 +133,25 @@ __device__ __forceinline__ void hist_add(unsigned* h, unsigned bin) {
   if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
 }
 
-template <int DT, bool MASK>
+// arccos for the SAM mean.  Spectral angles of decoded imagery are small, so c sits next to 1 where
+// 1-c is exact (Sterbenz) and acos(c) = 2*asin(sqrt((1-c)/2)); the odd series below is accurate to
+// < 1e-16 relative for angles up to 0.12 rad.  Anything else takes libdevice's acos.
+__device__ __forceinline__ double acos_sam(double c) {
+  const double e = 1.0 - c;
+  if (e >= 0.0 && e < 0.0072) {
+    const double s2 = 0.5 * e, s = __dsqrt_rn(s2);
+    double p = 945.0 / 42240.0;
+    p = fma(p, s2, 105.0 / 3456.0);
+    p = fma(p, s2, 15.0 / 336.0);
+    p = fma(p, s2, 3.0 / 40.0);
+    p = fma(p, s2, 1.0 / 6.0);
+    p = fma(p, s2, 1.0);
+    return 2.0 * s * p;
+  }
+  return acos(c);
+}
+
+template <int DT, bool MASK, bool ERR>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_bip_kernel(FusedArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -142,15 +165,16 @@ fused_bip_kernel(FusedArgs g) {
   const uint32_t cube_bytes = (uint32_t)P * (uint32_t)B * 2u;     // one cube's share of a stage
   const uint32_t stage_bytes = 2u * cube_bytes;
   constexpr uint32_t OFS = DT == DM_I16 ? 0x80008000u : 0u;
+  constexpr bool TRACK = MASK || DT == DM_I16;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBandWarps + kPixelWarps); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kBandWarps + kPixelWarps / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 256) { h8g[tid] = 0; h8z[tid] = 0; }
   __syncthreads();
 
-  // tiles of this CTA: full tiles t = blockIdx.x + k*gridDim.x, then (last CTA-slot) the tail tile
+  // tiles of this CTA: full tiles t = blockIdx.x + k*gridDim.x, then (one CTA) the tail tile
   const int64_t total_tiles = g.ntiles + (g.tail_pixels ? 1 : 0);
   const char* ref8 = static_cast<const char*>(g.ref);
   const char* tst8 = static_cast<const char*>(g.tst);
@@ -161,7 +185,7 @@ fused_bip_kernel(FusedArgs g) {
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
-      mbar_wait(&empty_bar[s], ph ^ 1u);             // first pass: passes immediately
+      mbar_wait(&empty_bar[s], ph ^ 1u);             // first pass over the ring: passes immediately
       unsigned char* dst = smem + (size_t)s * stage_bytes;
       const int64_t off = t * (int64_t)cube_bytes;
       if (t < g.ntiles) {
@@ -193,7 +217,7 @@ fused_bip_kernel(FusedArgs g) {
     BandAcc a[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[j].reset();
-    uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0;
+    uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
     long long n = 0;
     int since_spill = 0;
     bool any = false;
@@ -205,23 +229,31 @@ fused_bip_kernel(FusedArgs g) {
       for (int k = 0; k < 2; ++k) {
         // data-range scan on the raw reference words (unmasked)
         orbits |= xaw[k] | xbw[k];
-        const uint32_t ua = xaw[k] ^ OFS, ub = xbw[k] ^ OFS;
+        const uint32_t ua = xaw[k] ^ OFS, ub = xbw[k] ^ OFS, va = yaw[k] ^ OFS, vb = ybw[k] ^ OFS;
         umax = __vimax3_u16x2(umax, ua, ub);
         if (DT == DM_I16) umin = __vimin3_u16x2(umin, ua, ub);
+        if (!TRACK) ymax = __vimax3_u16x2(ymax, va, vb);
         uint32_t x0 = __byte_perm(ua, ub, 0x5410), x1 = __byte_perm(ua, ub, 0x7632);
-        uint32_t y0 = __byte_perm(yaw[k] ^ OFS, ybw[k] ^ OFS, 0x5410), y1 = __byte_perm(yaw[k] ^ OFS, ybw[k] ^ OFS, 0x7632);
+        uint32_t y0 = __byte_perm(va, vb, 0x5410), y1 = __byte_perm(va, vb, 0x7632);
         if (MASK) { x0 &= m; x1 &= m; y0 &= m; y1 &= m; }
         if (DT == DM_I16) {
           // np.abs semantics on the signed samples (wrapping abs of -32768 never wins)
-          const uint32_t sx0 = (x0 ^ OFS) & (MASK ? m : 0xffffffffu), sx1 = (x1 ^ OFS) & (MASK ? m : 0xffffffffu);
-          const uint32_t sy0 = (y0 ^ OFS) & (MASK ? m : 0xffffffffu), sy1 = (y1 ^ OFS) & (MASK ? m : 0xffffffffu);
+          const uint32_t mm = MASK ? m : 0xffffffffu;
+          const uint32_t sx0 = (x0 ^ OFS) & mm, sx1 = (x1 ^ OFS) & mm, sy0 = (y0 ^ OFS) & mm, sy1 = (y1 ^ OFS) & mm;
           maxsel_s = __vimax3_s16x2(maxsel_s, __vabs2(sx0), __vabs2(sy0));
           maxsel_s = __vimax3_s16x2(maxsel_s, __vabs2(sx1), __vabs2(sy1));
         }
-        band_word<PAIR>(a[2 * k], x0, y0, maxsel_u);
-        band_word<PAIR>(a[2 * k + 1], x1, y1, maxsel_u);
+        band_word<PAIR, TRACK>(a[2 * k], x0, y0, maxsel_u);
+        band_word<PAIR, TRACK>(a[2 * k + 1], x1, y1, maxsel_u);
       }
     };
+
+    // shared-memory walk of this thread: pair q = slot, slot+nslots, ... ; pixel 2q sits at byte
+    // 2q*W*4 of the cube's share, its partner W*4 bytes further, the next pair pstep further
+    const uint32_t w4 = (uint32_t)W * 4u;
+    const uint32_t pstep = 2u * (uint32_t)nslots * w4;
+    const uint32_t first = (2u * (uint32_t)slot * (uint32_t)W + (uint32_t)col) * 4u;
+    const int full_steps = active ? ((P >> 1) - slot + nslots - 1) / nslots : 0;   // steps of a full tile
 
     int it = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -230,35 +262,37 @@ fused_bip_kernel(FusedArgs g) {
       const int cnt = t < g.ntiles ? P : g.tail_pixels;
       mbar_wait(&full_bar[s], ph);
       if (active) {
-        const unsigned char* xs = smem + (size_t)s * stage_bytes;
-        const unsigned char* ys = xs + cube_bytes;
+        const unsigned char* xs = smem + (size_t)s * stage_bytes + first;
         const uint8_t* pl = MASK ? g.plane + t * (int64_t)P : nullptr;
         any = true;
-        const int npairs = cnt >> 1;
-        for (int q = slot; q < npairs; q += nslots) {
-          const int pa = 2 * q, pb = pa + 1;
-          const uint2 xa = *reinterpret_cast<const uint2*>(xs + ((size_t)pa * W + col) * 4);
-          const uint2 xb = *reinterpret_cast<const uint2*>(xs + ((size_t)pb * W + col) * 4);
-          const uint2 ya = *reinterpret_cast<const uint2*>(ys + ((size_t)pa * W + col) * 4);
-          const uint2 yb = *reinterpret_cast<const uint2*>(ys + ((size_t)pb * W + col) * 4);
+        const int steps = cnt == P ? full_steps : ((cnt >> 1) - slot + nslots - 1) / nslots;
+        if (since_spill + steps > 127) {
+          since_spill = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) a[j].spill();
+        }
+        since_spill += steps > 0 ? steps : 0;
+        if (!MASK) n += steps > 0 ? 2 * steps : 0;
+#pragma unroll 2
+        for (int i = 0; i < steps; ++i) {
+          const unsigned char* px = xs + (uint32_t)i * pstep;
+          const uint2 xa = *reinterpret_cast<const uint2*>(px);
+          const uint2 xb = *reinterpret_cast<const uint2*>(px + w4);
+          const uint2 ya = *reinterpret_cast<const uint2*>(px + cube_bytes);
+          const uint2 yb = *reinterpret_cast<const uint2*>(px + cube_bytes + w4);
           uint32_t m = 0xffffffffu;
           if (MASK) {
-            m = ((pl[pa] & DM_VALID_METRICS) ? 0xffffu : 0u) | ((pl[pb] & DM_VALID_METRICS) ? 0xffff0000u : 0u);
+            const int pa = 2 * (slot + i * nslots);
+            m = ((pl[pa] & DM_VALID_METRICS) ? 0xffffu : 0u) | ((pl[pa + 1] & DM_VALID_METRICS) ? 0xffff0000u : 0u);
             n += (m & 1u) + (m >> 31);
-          } else {
-            n += 2;
           }
           pair_step(xa, xb, ya, yb, m, std::true_type());
-          if (++since_spill >= 127) {
-            since_spill = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j].spill();
-          }
         }
         if ((cnt & 1) && slot == 0) {                // odd leftover pixel of the tail tile
           const int pa = cnt - 1;
-          const uint2 xa = *reinterpret_cast<const uint2*>(xs + ((size_t)pa * W + col) * 4);
-          const uint2 ya = *reinterpret_cast<const uint2*>(ys + ((size_t)pa * W + col) * 4);
+          const unsigned char* px = smem + (size_t)s * stage_bytes + ((size_t)pa * W + col) * 4;
+          const uint2 xa = *reinterpret_cast<const uint2*>(px);
+          const uint2 ya = *reinterpret_cast<const uint2*>(px + cube_bytes);
           uint32_t m = 0xffffffffu;
           if (MASK) m = (pl[pa] & DM_VALID_METRICS) ? 0xffffffffu : 0u;
           n += m ? 1 : 0;
@@ -273,41 +307,47 @@ fused_bip_kernel(FusedArgs g) {
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) a[j].spill();
-    // ---- combine the band group through shared memory (stage memory is free once every tile is done)
+    if (!TRACK) maxsel_u = vmaxu2(umax, ymax);       // unmasked uint16: max over everything read
+    // ---- combine the band group through shared memory (stage memory is free once every tile is done).
+    // No atomics: every thread stores its 8 per-band values at [quantity][j][slot][column pair]
+    // (consecutive lanes -> consecutive 8-byte words), then one thread per band adds the slots.
     asm volatile("bar.sync 1, %0;" ::"r"(kBandThreads + kPixelThreads));       // consumers only
-    unsigned long long* sh_sums = reinterpret_cast<unsigned long long*>(smem);     // [B][8]
-    int* sh_maxd = reinterpret_cast<int*>(sh_sums + (size_t)B * DM_NSTAT);         // [B]
-    int* sh_cube = sh_maxd + B;                                                     // [8]
-    for (int i = ts; i < B * DM_NSTAT; i += kBandThreads) sh_sums[i] = 0;
-    for (int i = ts; i < B; i += kBandThreads) sh_maxd[i] = 0;
+    unsigned long long* sh_part = reinterpret_cast<unsigned long long*>(smem);      // [8][4][nslots*tpp]
+    const int lanes_used = nslots * tpp;
+    __shared__ int sh_cube[8];
     if (ts < 8) sh_cube[ts] = ts == 2 ? 0x7fffffff : (ts == 0 ? (int)0x80000000 : 0);
-    asm volatile("bar.sync 2, %0;" ::"r"(kBandThreads));
     if (active) {
+      const int me = slot * tpp + (col >> 1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        unsigned long long* S = sh_sums + (size_t)(2 * col + j) * DM_NSTAT;
-        if (n) atomicAdd(S + DM_S_N, (unsigned long long)n);
-        if (a[j].t_abs) atomicAdd(S + DM_S_ABS, a[j].t_abs);
-        if (a[j].t_x) atomicAdd(S + DM_S_X, a[j].t_x);
-        if (a[j].t_y) atomicAdd(S + DM_S_Y, a[j].t_y);
-        if (a[j].t_xx) atomicAdd(S + DM_S_XX, a[j].t_xx);
-        if (a[j].t_yy) atomicAdd(S + DM_S_YY, a[j].t_yy);
-        if (a[j].t_xy) atomicAdd(S + DM_S_XY, a[j].t_xy);
-        atomicMax(sh_maxd + 2 * col + j, hmax2(a[j].maxd));
-      }
-      if (any) {
-        atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(maxsel_s) : hmax2(maxsel_u));
-        atomicMax(sh_cube + 1, hmax2(umax));
-        atomicMin(sh_cube + 2, hmin2(umin));
-        atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (orbits | (orbits >> 16)) & 0xffffu);
-        sh_cube[4] = 1;
+        unsigned long long* d = sh_part + (size_t)j * lanes_used + me;
+        const size_t q = (size_t)4 * lanes_used;
+        d[0 * q] = (unsigned long long)n;
+        d[1 * q] = a[j].t_x; d[2 * q] = a[j].t_y; d[3 * q] = a[j].t_xx; d[4 * q] = a[j].t_yy; d[5 * q] = a[j].t_xy;
+        d[6 * q] = a[j].t_abs; d[7 * q] = (unsigned long long)hmax2(a[j].maxd);
       }
     }
     asm volatile("bar.sync 2, %0;" ::"r"(kBandThreads));
+    if (active && any) {
+      atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(maxsel_s) : hmax2(maxsel_u));
+      atomicMax(sh_cube + 1, hmax2(umax));
+      atomicMin(sh_cube + 2, hmin2(umin));
+      atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (orbits | (orbits >> 16)) & 0xffffu);
+      sh_cube[4] = 1;
+    }
     for (int b = ts; b < B; b += kBandThreads) {
-      const unsigned long long* S = sh_sums + (size_t)b * DM_NSTAT;
-      long long nn = (long long)S[DM_S_N], sx = (long long)S[DM_S_X], sy = (long long)S[DM_S_Y];
-      long long sxx = (long long)S[DM_S_XX], syy = (long long)S[DM_S_YY], sxy = (long long)S[DM_S_XY];
+      const int cp = b >> 2, j = b & 3;
+      const size_t q = (size_t)4 * lanes_used;
+      unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
+      int md = 0;
+      for (int sl = 0; sl < nslots; ++sl) {
+        const unsigned long long* d = sh_part + (size_t)j * lanes_used + sl * tpp + cp;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += d[k * q];
+        md = max(md, (int)d[7 * q]);
+      }
+      long long nn = (long long)v[0], sx = (long long)v[1], sy = (long long)v[2];
+      long long sxx = (long long)v[3], syy = (long long)v[4], sxy = (long long)v[5];
       if (DT == DM_I16) {
         const long long c = 32768, c2 = 32768ll * 32768ll;
         const long long xx = sxx - 2 * c * sx + c2 * nn, yy = syy - 2 * c * sy + c2 * nn;
@@ -316,7 +356,7 @@ fused_bip_kernel(FusedArgs g) {
       }
       int64_t* O = g.sums + (int64_t)b * DM_NSTAT;
       if (nn) atomic_add_i64(O + DM_S_N, nn);
-      if (S[DM_S_ABS]) atomic_add_i64(O + DM_S_ABS, (long long)S[DM_S_ABS]);
+      if (v[6]) atomic_add_i64(O + DM_S_ABS, (long long)v[6]);
       if (sx) atomic_add_i64(O + DM_S_X, sx);
       if (sy) atomic_add_i64(O + DM_S_Y, sy);
       if (sxx) atomic_add_i64(O + DM_S_XX, sxx);
@@ -324,8 +364,9 @@ fused_bip_kernel(FusedArgs g) {
       if (sxy) atomic_add_i64(O + DM_S_XY, sxy);
       const long long sse = sxx + syy - 2 * sxy;
       if (sse) atomic_add_i64(O + DM_S_SSE, sse);
-      if (sh_maxd[b]) atomic_max_i64(g.maxs + (int64_t)b * DM_NSTAT + DM_M_MAXERR, sh_maxd[b]);
+      if (md) atomic_max_i64(g.maxs + (int64_t)b * DM_NSTAT + DM_M_MAXERR, md);
     }
+    asm volatile("bar.sync 2, %0;" ::"r"(kBandThreads));
     if (ts == 0 && sh_cube[4]) {
       int64_t* M = g.maxs;
       if (DT == DM_I16) {
@@ -341,22 +382,26 @@ fused_bip_kernel(FusedArgs g) {
     }
   } else {
     // ------------------------------------------------------------------ pixel group
-    const int tp = tid - 32 - kBandThreads;          // 0..127 <-> pixel of the tile
+    // thread <-> pixel; the group is two halves of kTilePixels threads and half h takes the tiles
+    // with (it & 1) == h, so every lane is busy in the float64 finish of its own pixel.
+    // (Measured alternatives, same data: two lanes per pixel with an early stage release 243 us,
+    // the same with the finish deferred by one tile 227 us, this mapping 206 us.)
+    const int tg = tid - 32 - kBandThreads;          // 0..127
+    const int half = tg / kTilePixels;
+    const int tp = tg - half * kTilePixels;          // pixel of the tile
     double s_acos = 0.0, s_n = 0.0;
-    const bool want_err = g.errmax || g.err8_g || g.err8_z;
     int it = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != half) continue;
       const int s = it % kStages;
       const uint32_t ph = (uint32_t)((it / kStages) & 1);
       const int cnt = t < g.ntiles ? P : g.tail_pixels;
       mbar_wait(&full_bar[s], ph);
+      uint32_t emax = 0;
+      uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0, sx = 0, sy = 0;
       if (tp < cnt) {
         const unsigned char* xs = smem + (size_t)s * stage_bytes + (size_t)tp * W * 4;
         const unsigned char* ys = xs + cube_bytes;
-        const int64_t p = t * (int64_t)P + tp;
-        const uint8_t v = MASK ? g.plane[p] : (uint8_t)0xff;
-        uint32_t emax = 0;
-        uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0, sx = 0, sy = 0;
 #pragma unroll 5
         for (int j = 0; j < (W >> 1); ++j) {
           const uint2 xv = *reinterpret_cast<const uint2*>(xs + 8 * j);
@@ -365,7 +410,7 @@ fused_bip_kernel(FusedArgs g) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint32_t x = xw[k], y = yw[k];
-            emax = vmaxu2(emax, vmaxu2(x, y) - vminu2(x, y));
+            if (ERR) emax = vmaxu2(emax, vmaxu2(x, y) - vminu2(x, y));
             const uint32_t px = __byte_perm(x, 0, 0x3120), py = __byte_perm(y, 0, 0x3120);
             xxl = dp2a_lo(x, px, xxl); xxh = dp2a_hi(x, px, xxh);
             yyl = dp2a_lo(y, py, yyl); yyh = dp2a_hi(y, py, yyh);
@@ -373,7 +418,14 @@ fused_bip_kernel(FusedArgs g) {
             if (DT == DM_I16) { sx = dp2a_lo(x, 0x0101u, sx); sy = dp2a_lo(y, 0x0101u, sy); }
           }
         }
-        if (want_err) {
+      }
+      // the stage is no longer needed: release it before the per-pixel float64 work
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (tp < cnt) {
+        const int64_t p = t * (int64_t)P + tp;
+        const uint8_t v = MASK ? g.plane[p] : (uint8_t)0xff;
+        if (ERR) {
           int e = (v & DM_VALID_QUICKLOOK) ? hmax2(emax) : 0;           // quicklooks.py:134
           if (g.errmax) g.errmax[p] = (uint16_t)e;
           if (g.err8_g) {
@@ -388,25 +440,24 @@ fused_bip_kernel(FusedArgs g) {
           }
         }
         if (g.want_sam && (v & DM_VALID_SPECTRAL)) {
-          long long na2 = (long long)xxl + ((long long)xxh << 8);
-          long long nr2 = (long long)yyl + ((long long)yyh << 8);
-          long long dot = (long long)xyl + ((long long)xyh << 8);
+          // lo + 256*hi: both halves < 2^32 and the sum < 2^53, so float64 holds it exactly
+          double na2 = fma((double)xxh, 256.0, (double)xxl);
+          double nr2 = fma((double)yyh, 256.0, (double)yyl);
+          double dot = fma((double)xyh, 256.0, (double)xyl);
           if (DT == DM_I16) {
-            const long long c = 32768, c2B = 32768ll * 32768ll * B;
-            dot = dot - c * ((long long)sx + sy) + c2B;
-            na2 = na2 - 2 * c * (long long)sx + c2B;
-            nr2 = nr2 - 2 * c * (long long)sy + c2B;
+            const double c = 32768.0, c2B = 32768.0 * 32768.0 * (double)B, fx = (double)sx, fy = (double)sy;
+            dot = dot - c * (fx + fy) + c2B;             // all terms exact integers below 2^53
+            na2 = na2 - 2.0 * c * fx + c2B;
+            nr2 = nr2 - 2.0 * c * fy + c2B;
           }
-          const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
-          const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
-          double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
+          const double na = __dadd_rn(__dsqrt_rn(na2), 1e-12);
+          const double nr = __dadd_rn(__dsqrt_rn(nr2), 1e-12);
+          double c = __ddiv_rn(dot, __dmul_rn(na, nr));
           c = fmin(1.0, fmax(-1.0, c));
-          s_acos += acos(c);
+          s_acos += acos_sam(c);
           s_n += 1.0;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
     asm volatile("bar.sync 1, %0;" ::"r"(kBandThreads + kPixelThreads));       // pairs with the band group
     // deterministic reduction of the float partials: warp shuffle tree, then warps in order
@@ -414,14 +465,14 @@ fused_bip_kernel(FusedArgs g) {
     const int pw = warp - 1 - kBandWarps;
     if (lane == 0) { red[0][pw] = s_acos; red[2][pw] = s_n; }
     asm volatile("bar.sync 3, %0;" ::"r"(kPixelThreads));
-    if (tp == 0 && g.spec_out) {
+    if (tg == 0 && g.spec_out) {
       double t0 = 0, t2 = 0;
       for (int w = 0; w < kPixelWarps; ++w) { t0 += red[0][w]; t2 += red[2][w]; }
       g.spec_out[3 * blockIdx.x + 0] = t0; g.spec_out[3 * blockIdx.x + 1] = 0.0; g.spec_out[3 * blockIdx.x + 2] = t2;
     }
     if (blockIdx.x == 0 && g.spec_out)       // unused slots of the fixed-size partial array
-      for (int i = 3 * gridDim.x + tp; i < 3 * kMaxSpecBlocks; i += kPixelThreads) g.spec_out[i] = 0.0;
-    for (int i = tp; i < 256; i += kPixelThreads) {
+      for (int i = 3 * gridDim.x + tg; i < 3 * kMaxSpecBlocks; i += kPixelThreads) g.spec_out[i] = 0.0;
+    for (int i = tg; i < 256; i += kPixelThreads) {
       if (g.hist8_g && h8g[i]) atomic_add_i64(g.hist8_g + i, h8g[i]);
       if (g.hist8_z && h8z[i]) atomic_add_i64(g.hist8_z + i, h8z[i]);
     }
@@ -448,7 +499,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (want_sam && !spectral_out) return fail(DM_EARG, "dm_fused_bip: spectral_out is null");
   FusedArgs g;
   g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
-  int P = kPixelThreads;                               // 128 pixels per tile when they fit a stage
+  int P = kTilePixels;                                 // 64 pixels per tile when they fit a stage
   while ((int64_t)P * B * 4 > kStageBytesMax) P >>= 1;
   g.P = P;                                             // P*B*2 is a multiple of 16 (P even, B % 4 == 0)
   g.ntiles = g.npix / P;
@@ -464,16 +515,22 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   size_t smem = (size_t)kStages * 2 * P * B * 2;
-  const size_t need_combine = (size_t)B * DM_NSTAT * 8 + (size_t)B * 4 + 64;
+  const size_t need_combine = (size_t)8 * 4 * kBandThreads * 8;   // [8][4][<=192] uint64 partials
   if (smem < need_combine) smem = need_combine;
-#define DM_FUSED(DT, MASK)                                                                            \
+#define DM_FUSED(DT, MASK, ERR)                                                                       \
   do {                                                                                                \
-    auto k = fused_bip_kernel<DT, MASK>;                                                              \
+    auto k = fused_bip_kernel<DT, MASK, ERR>;                                                         \
     DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     k<<<(unsigned)grid, kThreads, smem, s>>>(g);                                                      \
   } while (0)
-  if (p.dtype == DM_U16) { if (plane) DM_FUSED(DM_U16, true); else DM_FUSED(DM_U16, false); }
-  else { if (plane) DM_FUSED(DM_I16, true); else DM_FUSED(DM_I16, false); }
+  const bool err = errmax_out || err8_g || err8_z;
+  if (p.dtype == DM_U16) {
+    if (plane) { if (err) DM_FUSED(DM_U16, true, true); else DM_FUSED(DM_U16, true, false); }
+    else { if (err) DM_FUSED(DM_U16, false, true); else DM_FUSED(DM_U16, false, false); }
+  } else {
+    if (plane) { if (err) DM_FUSED(DM_I16, true, true); else DM_FUSED(DM_I16, true, false); }
+    else { if (err) DM_FUSED(DM_I16, false, true); else DM_FUSED(DM_I16, false, false); }
+  }
 #undef DM_FUSED
   DM_LAUNCH_CHECK("fused_bip");
   return DM_OK;

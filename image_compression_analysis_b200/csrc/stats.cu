@@ -427,15 +427,13 @@ __global__ void __launch_bounds__(384)
 stats_bip_packed(StatsArgs g, BipGeom geo) {
   constexpr int NB = 2 * C;      // bands per thread
   constexpr int U = 4;           // pixel-pair steps in flight
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int B = (int)g.bands, K = g.hist_bins;
-  unsigned long long* sh_sums = reinterpret_cast<unsigned long long*>(smem_raw);   // [B][DM_NSTAT]
-  int* sh_maxd = reinterpret_cast<int*>(sh_sums + (size_t)B * DM_NSTAT);          // [B]
-  int* sh_cube = sh_maxd + B;                                                      // [8]
-  unsigned* sh_hist = reinterpret_cast<unsigned*>(sh_cube + 8);                    // HIST: [K][B]
+  // [8 ints cube-wide | region shared by the histogram (main loop) and the combine partials (end)]
+  int* sh_cube = reinterpret_cast<int*>(smem_raw);                                 // [8] (+ pad to 64 B)
+  unsigned long long* sh_sums = reinterpret_cast<unsigned long long*>(smem_raw + 64);   // [8][NB][ppb*tpp] partials
+  unsigned* sh_hist = reinterpret_cast<unsigned*>(smem_raw + 64);                  // HIST: [K][B]
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < B * DM_NSTAT; i += nt) sh_sums[i] = 0;
-  for (int i = tid; i < B; i += nt) sh_maxd[i] = 0;
   if (tid < 8) sh_cube[tid] = tid == 2 ? 0x7fffffff : (tid == 0 ? (int)0x80000000 : 0);
   if (HIST) for (int i = tid; i < K * B; i += nt) sh_hist[i] = 0;
   __syncthreads();
@@ -540,45 +538,55 @@ stats_bip_packed(StatsArgs g, BipGeom geo) {
 #pragma unroll
   for (int j = 0; j < NB; ++j) a[j].spill();
 
-  // combine: threads holding the same band meet in shared memory (once per kernel)
-  if (prow < geo.ppb) {
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      unsigned long long* S = sh_sums + (size_t)(2 * col + j) * DM_NSTAT;
-      if (n) atomicAdd(S + DM_S_N, (unsigned long long)n);
-      if (a[j].t_abs) atomicAdd(S + DM_S_ABS, a[j].t_abs);
-      if (a[j].t_xx) atomicAdd(S + DM_S_XX, a[j].t_xx);
-      if (MOMENTS) {
-        if (a[j].t_x) atomicAdd(S + DM_S_X, a[j].t_x);
-        if (a[j].t_y) atomicAdd(S + DM_S_Y, a[j].t_y);
-        if (a[j].t_yy) atomicAdd(S + DM_S_YY, a[j].t_yy);
-        if (a[j].t_xy) atomicAdd(S + DM_S_XY, a[j].t_xy);
-      }
-      atomicMax(sh_maxd + 2 * col + j, hmax2(a[j].maxd));
-    }
-    if (any) {
-      atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(c.maxsel) : hmax2(c.maxsel));
-      atomicMax(sh_cube + 1, hmax2(c.umax));
-      atomicMin(sh_cube + 2, hmin2(c.umin));
-      atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (c.orbits | (c.orbits >> 16)) & 0xffffu);
-      sh_cube[4] = 1;
-    }
-  }
-  __syncthreads();
-  for (int b = tid; b < B; b += nt) {
-    const unsigned long long* S = sh_sums + (size_t)b * DM_NSTAT;
-    red_band<DT, MOMENTS>(g, b, (long long)S[DM_S_N], (long long)S[DM_S_ABS], (long long)S[DM_S_X],
-                          (long long)S[DM_S_Y], (long long)S[DM_S_XX], (long long)S[DM_S_YY],
-                          (long long)S[DM_S_XY], sh_maxd[b]);
-  }
-  if (tid == 0) red_cube<DT>(g, sh_cube[0], sh_cube[1], sh_cube[2], (unsigned)sh_cube[3], sh_cube[4] != 0);
-  if (HIST) {
+  if (HIST) {       // flush the histogram first: its memory is reused by the combine below
+    __syncthreads();
     for (int i = tid; i < K * B; i += nt) {
       const int k = i / B, b = i - k * B;
       const unsigned cnt = sh_hist[i];
       if (cnt) atomic_add_i64(g.hist + (int64_t)b * K + k, (long long)cnt);
     }
+    __syncthreads();
   }
+  // combine (once per kernel), without atomics: every thread stores its per-band values at
+  // [quantity][j][pixel row][column group] (consecutive lanes -> consecutive 8-byte words), then one
+  // thread per band adds the pixel rows
+  {
+    unsigned long long* sh_part = sh_sums;             // [8][NB][ppb*tpp] uint64 (sized by the host)
+    const int lanes_used = geo.ppb * geo.tpp;
+    const size_t q = (size_t)NB * lanes_used;
+    if (prow < geo.ppb) {
+      const int me = prow * geo.tpp + col / C;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        unsigned long long* d = sh_part + (size_t)j * lanes_used + me;
+        d[0 * q] = (unsigned long long)n;
+        d[1 * q] = a[j].t_x; d[2 * q] = a[j].t_y; d[3 * q] = a[j].t_xx; d[4 * q] = a[j].t_yy; d[5 * q] = a[j].t_xy;
+        d[6 * q] = a[j].t_abs; d[7 * q] = (unsigned long long)hmax2(a[j].maxd);
+      }
+      if (any) {
+        atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(c.maxsel) : hmax2(c.maxsel));
+        atomicMax(sh_cube + 1, hmax2(c.umax));
+        atomicMin(sh_cube + 2, hmin2(c.umin));
+        atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (c.orbits | (c.orbits >> 16)) & 0xffffu);
+        sh_cube[4] = 1;
+      }
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += nt) {
+      const int cg = b / NB, j = b - cg * NB;
+      unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
+      int md = 0;
+      for (int r = 0; r < geo.ppb; ++r) {
+        const unsigned long long* d = sh_part + (size_t)j * lanes_used + r * geo.tpp + cg;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += d[k * q];
+        md = max(md, (int)d[7 * q]);
+      }
+      red_band<DT, MOMENTS>(g, b, (long long)v[0], (long long)v[6], (long long)v[1], (long long)v[2], (long long)v[3],
+                            (long long)v[4], (long long)v[5], md);
+    }
+  }
+  if (tid == 0) red_cube<DT>(g, sh_cube[0], sh_cube[1], sh_cube[2], (unsigned)sh_cube[3], sh_cube[4] != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -691,8 +699,9 @@ int run_bip(const StatsArgs& g, cudaStream_t s) {
   const int threads = geo.tpp * ppb;
   geo.ngroups = g.npix / (2 * ppb);
   auto kernel = stats_bip_packed<DT, MASK, MOMENTS, HIST, C>;
-  size_t smem = (size_t)B * DM_NSTAT * 8 + (size_t)B * 4 + 8 * 4;
-  if (HIST) smem += (size_t)g.hist_bins * B * sizeof(unsigned);
+  size_t smem = (size_t)8 * (2 * C) * threads * 8;
+  if (HIST && (size_t)g.hist_bins * B * sizeof(unsigned) > smem) smem = (size_t)g.hist_bins * B * sizeof(unsigned);
+  smem += 64;
   if (smem > 48 * 1024)
     DM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
@@ -782,8 +791,7 @@ int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, 
     if (packed) {
       bip_cols = (B % 4 == 0 && ra % 8 == 0 && ta % 8 == 0) ? 2 : 1;
       if ((B / 2) / bip_cols > 384) packed = false;
-      const size_t smem = (size_t)B * DM_NSTAT * 8 + (size_t)B * 4 + 32 + (size_t)hist_bins * B * 4;
-      if (smem > 200 * 1024) packed = false;
+      if ((size_t)hist_bins * B * 4 > 200 * 1024) packed = false;
     }
   }
   if (!packed) {
