@@ -27,7 +27,43 @@ bip_to_bsq_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t bands,
   }
 }
 
+// world gathered partial vectors -> one (see dm_combine_partials in dm_b200.h)
+__global__ void __launch_bounds__(256)
+combine_partials_kernel(const long long* __restrict__ gathered, int world, int64_t n_sum, int64_t n_max, int64_t n_f64,
+                        long long* __restrict__ out) {
+  const int64_t len = n_sum + n_max + n_f64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_sum) {
+      long long v = 0;
+      for (int r = 0; r < world; ++r) v += gathered[(int64_t)r * len + i];
+      out[i] = v;
+    } else if (i < n_sum + n_max) {
+      long long v = gathered[i];
+      for (int r = 1; r < world; ++r) v = max(v, gathered[(int64_t)r * len + i]);
+      out[i] = v;
+    } else {
+      double v = 0.0;
+      for (int r = 0; r < world; ++r) v += __longlong_as_double(gathered[(int64_t)r * len + i]);   // rank order
+      out[i] = __double_as_longlong(v);
+    }
+  }
+}
+
 }  // namespace
+
+int launch_combine_partials(const void* gathered, int world, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out,
+                            cudaStream_t s) {
+  if (!gathered || !out) return fail(DM_EARG, "dm_combine_partials: null pointer");
+  if (world < 1 || n_sum < 0 || n_max < 0 || n_f64 < 0) return fail(DM_EARG, "dm_combine_partials: bad sizes");
+  const int64_t len = n_sum + n_max + n_f64;
+  if (len == 0) return DM_OK;
+  int64_t grid = (len + 255) / 256;
+  if (grid > 1024) grid = 1024;
+  combine_partials_kernel<<<(unsigned)grid, 256, 0, s>>>(static_cast<const long long*>(gathered), world, n_sum, n_max,
+                                                        n_f64, static_cast<long long*>(out));
+  DM_LAUNCH_CHECK("combine_partials");
+  return DM_OK;
+}
 
 int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands, int64_t rows, int64_t width,
                       cudaStream_t s) {

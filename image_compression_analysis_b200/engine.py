@@ -183,6 +183,7 @@ class Partials:
     planes: Dict[str, torch.Tensor] = field(default_factory=dict)   # errmax / err8_g / err8_z / valid
     np_dtype: str = "uint16"
     used_mask: bool = False
+    flat: Optional[torch.Tensor] = None     # the buffer isum / imax / fsum are views of
 
     # layout helpers ------------------------------------------------------------------------
     @staticmethod
@@ -191,10 +192,17 @@ class Partials:
 
     @staticmethod
     def allocate(bands: int, hist_bins: int, device, np_dtype: str) -> "Partials":
+        """One flat 8-byte-word buffer [isum | imax | fsum]; the three vectors are views of it, so the
+        multi-GPU exchange is a single all-gather and the host read-back a single copy."""
         ni, nm, nf = Partials.sizes(bands, hist_bins)
-        return Partials(bands, hist_bins, torch.zeros(ni, dtype=torch.int64, device=device),
-                        torch.zeros(nm, dtype=torch.int64, device=device),
-                        torch.zeros(nf, dtype=torch.float64, device=device), {}, np_dtype)
+        flat = torch.zeros(ni + nm + nf, dtype=torch.int64, device=device)
+        P = Partials(bands, hist_bins, flat[:ni], flat[ni:ni + nm], flat[ni + nm:].view(torch.float64), {}, np_dtype)
+        P.flat = flat
+        return P
+
+    def zero_(self) -> "Partials":
+        self.flat.zero_()
+        return self
 
     def _o(self):
         B, K = self.bands, self.hist_bins
@@ -233,9 +241,18 @@ class Partials:
         """Combine the partials of all ranks in place: int64 SUM, int64 MAX, float64 SUM.
 
         The only exchange step of the path: payload B*(8+K+8+3)*8 bytes, latency
-        bound.  Works on NCCL (device tensors) and on gloo (CPU tensors, used by the CPU tests)."""
+        bound.  On CUDA tensors it is ONE NCCL all-gather of the flat buffer followed by
+        dm_combine_partials (float64 sums in rank order: bit-identical on every rank); on CPU
+        tensors (gloo, the CPU tests) three all-reduces."""
         import torch.distributed as dist
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return self
+        world = dist.get_world_size(group)
+        if self.flat is not None and self.flat.is_cuda:
+            gathered = torch.empty(world * self.flat.numel(), dtype=torch.int64, device=self.flat.device)
+            dist.all_gather_into_tensor(gathered, self.flat, group=group)
+            check(lib().dm_combine_partials(_ptr(gathered), world, self.isum.numel(), self.imax.numel(),
+                                            self.fsum.numel(), _ptr(self.flat), _stream_ptr()))
             return self
         works = [dist.all_reduce(self.isum, op=dist.ReduceOp.SUM, group=group, async_op=True),
                  dist.all_reduce(self.imax, op=dist.ReduceOp.MAX, group=group, async_op=True),
@@ -245,7 +262,8 @@ class Partials:
         return self
 
     def to_host(self) -> "HostPartials":
-        flat = torch.cat([self.isum, self.imax, self.fsum.view(torch.int64)]).cpu().numpy()
+        flat = (self.flat if self.flat is not None
+                else torch.cat([self.isum, self.imax, self.fsum.view(torch.int64)])).cpu().numpy()
         ni, nm = self.isum.numel(), self.imax.numel()
         return HostPartials(self.bands, self.hist_bins, flat[:ni].copy(), flat[ni:ni + nm].copy(),
                             flat[ni + nm:].view(np.float64).copy(), self.np_dtype, self.used_mask)

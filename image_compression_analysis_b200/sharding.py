@@ -99,3 +99,43 @@ def evaluate_strip(ref, tst, s: Strip, img_rows: int, layout: str, want, valid=N
     if reduce:
         P.allreduce_(group)
     return P
+
+
+class PipelinedCombiner:
+    """Overlap the combine of pair i with the kernels of pair i+1 (a sweep of independent pairs).
+
+    The allreduce of a pair's partials is a few KB and latency bound (~tens of microseconds), the
+    same order as a 64th of a kernel; issued on the compute stream it would serialise with the next
+    pair's kernels.  Here it runs on a side stream behind an event, so the compute stream only waits
+    when it is about to REUSE a partials buffer whose combine has not finished."""
+
+    def __init__(self, group=None):
+        import torch
+        self.group = group
+        self.stream = torch.cuda.Stream()
+        self._done = {}
+
+    def before_reuse(self, P) -> None:
+        """Call before zeroing / accumulating into P again on the compute stream."""
+        import torch
+        ev = self._done.pop(id(P), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def combine(self, P):
+        """Allreduce P after everything queued so far on the current (compute) stream."""
+        import torch
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            P.allreduce_(self.group)
+            done = torch.cuda.Event()
+            done.record()
+        self._done[id(P)] = done
+        return P
+
+    def wait_all(self) -> None:
+        import torch
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self._done.clear()

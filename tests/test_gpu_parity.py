@@ -300,3 +300,27 @@ def test_fused_bip_vs_oracle(dtype, B, H, W, amp, masked):
     sam_want = orc.sam_caseB(ref, dec, valid)
     sam_got = finish.finish_spectral(float(hf.spec[0]), 0.0, float(hf.spec[2]), None, H * W)["sam_deg"]
     assert _close(sam_got, sam_want), (sam_got, sam_want)
+
+
+def test_combine_partials_kernel():
+    """dm_combine_partials (the reduction after the multi-GPU all-gather) against numpy."""
+    import ctypes as C
+    import torch
+    from image_compression_analysis_b200 import _lib
+    rng = np.random.default_rng(3)
+    world, ns, nm, nf = 8, 1443, 1440, 543
+    L = ns + nm + nf
+    G = np.zeros((world, L), np.int64)
+    G[:, :ns + nm] = rng.integers(-2**40, 2**40, size=(world, ns + nm))
+    F = rng.standard_normal((world, nf)) * 1e6
+    G[:, ns + nm:] = F.view(np.int64)
+    g = torch.from_numpy(G).cuda()
+    out = torch.zeros(L, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().dm_combine_partials(C.c_void_p(g.data_ptr()), world, ns, nm, nf, C.c_void_p(out.data_ptr()), None))
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:ns], G[:, :ns].sum(0))
+    assert np.array_equal(o[ns:ns + nm], G[:, ns:ns + nm].max(0))
+    want = np.zeros(nf)
+    for r in range(world):
+        want = want + F[r]                      # rank order, like the kernel
+    assert np.array_equal(o[ns + nm:].view(np.float64), want)
