@@ -324,3 +324,24 @@ def test_combine_partials_kernel():
     for r in range(world):
         want = want + F[r]                      # rank order, like the kernel
     assert np.array_equal(o[ns + nm:].view(np.float64), want)
+
+
+def test_launcher_rebinds_the_reference_module(tmp_path):
+    """launcher.bind on a stand-in `run_codec` module: the reference's call sites
+    (tools/run_codec.py:518-526) reach the GPU functions with the reference's signatures."""
+    import types
+    from pathlib import Path
+    from oracle import rasterio_stub
+    rasterio_stub.install()
+    from image_compression_analysis_b200 import launcher
+    mod = types.ModuleType("run_codec")
+    launcher.bind(mod)
+    c = goldenio.load("a_gauss")
+    rasterio_stub.clear()
+    rasterio_stub.register("/mem/src.tif", c["ref"])
+    rasterio_stub.register("/mem/recon.tif", c["tst"])
+    row = mod.compute_metrics(Path("/mem/src.tif"), Path("/mem/recon.tif"), valid=None)
+    _check_metrics(row, c["compute_metrics"])
+    extra = mod.compute_sam_sid_lmse_caseB(Path("/mem/src.tif"), Path("/mem/recon.tif"), valid=None)
+    for k, w in c["sam_sid_lmse"].items():
+        assert _close(extra[k], w), k
