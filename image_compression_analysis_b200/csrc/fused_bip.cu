@@ -23,6 +23,7 @@
 // persistent: one CTA per SM, tiles strided over CTAs.  Shared-memory reads are conflict free for
 // EnMAP's 180 bands (pixel pitch 45 x 8 B, odd).  See DESIGN.md for the instruction budget.
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "dm_common.cuh"
@@ -31,9 +32,19 @@ namespace dm {
 
 namespace {
 
-constexpr int kBandWarps = 6, kPixelWarps = 4;
-constexpr int kBandThreads = kBandWarps * 32, kPixelThreads = kPixelWarps * 32;
-constexpr int kThreads = 32 + kBandThreads + kPixelThreads;     // 352
+// Band-group threads own C 32-bit columns (2C bands).  C = 1 needs half the accumulator registers, so
+// twelve band warps fit: with four pixel warps every scheduler (warp id mod 4) then hosts 3 band + 1
+// pixel warp.  With C = 2 (six band warps) two of the four schedulers carry 2 band + 1 pixel warp and
+// the others 1 + 1, and the tile barrier makes everyone wait for the loaded ones: measured 215 us vs
+// the balanced layout.
+constexpr int kPixelWarps = 4;
+constexpr int kPixelThreads = kPixelWarps * 32;
+template <int C> struct Shape {
+  static constexpr int kBandWarps = C == 2 ? 6 : 12;
+  static constexpr int kBandThreads = kBandWarps * 32;
+  static constexpr int kThreads = 32 + kBandThreads + kPixelThreads;     // 352 / 544
+};
+constexpr int kMaxBandThreads = 12 * 32;
 constexpr int kStages = 4;
 constexpr int kTilePixels = 64;                                  // pixels per tile (one half of the pixel group)
 constexpr int kStageBytesMax = 46080;                            // 2 cubes x 64 px x 180 bands x 2 B
@@ -54,6 +65,7 @@ struct FusedArgs {
   const uint8_t* lut_g; int cap_g; uint8_t* err8_g; int64_t* hist8_g;
   const uint8_t* lut_z; int cap_z; uint8_t* err8_z; int64_t* hist8_z;
   int want_sam;
+  int debug;                  // experiments only: 1 = producer skips the copies (compute-only timing)
   double* spec_out;           // [3 * kMaxSpecBlocks]
 };
 
@@ -151,9 +163,10 @@ __device__ __forceinline__ double acos_sam(double c) {
   return acos(c);
 }
 
-template <int DT, bool MASK, bool ERR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int DT, bool MASK, bool ERR, int C>
+__global__ void __launch_bounds__(Shape<C>::kThreads, 1)
 fused_bip_kernel(FusedArgs g) {
+  constexpr int kBandWarps = Shape<C>::kBandWarps, kBandThreads = Shape<C>::kBandThreads;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ unsigned h8g[256], h8z[256];
@@ -188,7 +201,9 @@ fused_bip_kernel(FusedArgs g) {
       mbar_wait(&empty_bar[s], ph ^ 1u);             // first pass over the ring: passes immediately
       unsigned char* dst = smem + (size_t)s * stage_bytes;
       const int64_t off = t * (int64_t)cube_bytes;
-      if (t < g.ntiles) {
+      if (g.debug == 1) {
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      } else if (t < g.ntiles) {
         if (lane == 0) {
           mbar_expect_tx(&full_bar[s], stage_bytes);
           bulk_g2s(dst, ref8 + off, cube_bytes, &full_bar[s]);
@@ -208,25 +223,26 @@ fused_bip_kernel(FusedArgs g) {
     }
   } else if (warp <= kBandWarps) {
     // ------------------------------------------------------------------ band group
-    const int ts = tid - 32;                         // 0..191
-    const int tpp = W >> 1;                          // threads per pixel (one 8-byte column pair each)
+    constexpr int NB = 2 * C;                        // bands per thread
+    const int ts = tid - 32;                         // 0..kBandThreads-1
+    const int tpp = W / C;                           // threads per pixel (C 32-bit columns each)
     const int nslots = kBandThreads / tpp;           // pixel pairs processed side by side
     const int slot = ts / tpp;
     const bool active = slot < nslots;
-    const int col = (ts - slot * tpp) * 2;           // first 32-bit column
-    BandAcc a[4];
+    const int col = (ts - slot * tpp) * C;           // first 32-bit column
+    BandAcc a[NB];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j].reset();
+    for (int j = 0; j < NB; ++j) a[j].reset();
     uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
     long long n = 0;
     int since_spill = 0;
     bool any = false;
 
-    auto pair_step = [&](const uint2 xa, const uint2 xb, const uint2 ya, const uint2 yb, uint32_t m, auto tag) {
+    auto pair_step = [&](const uint32_t (&xaw)[C], const uint32_t (&xbw)[C], const uint32_t (&yaw)[C],
+                         const uint32_t (&ybw)[C], uint32_t m, auto tag) {
       constexpr bool PAIR = decltype(tag)::value;
-      const uint32_t xaw[2] = {xa.x, xa.y}, xbw[2] = {xb.x, xb.y}, yaw[2] = {ya.x, ya.y}, ybw[2] = {yb.x, yb.y};
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < C; ++k) {
         // data-range scan on the raw reference words (unmasked)
         orbits |= xaw[k] | xbw[k];
         const uint32_t ua = xaw[k] ^ OFS, ub = xbw[k] ^ OFS, va = yaw[k] ^ OFS, vb = ybw[k] ^ OFS;
@@ -246,6 +262,10 @@ fused_bip_kernel(FusedArgs g) {
         band_word<PAIR, TRACK>(a[2 * k], x0, y0, maxsel_u);
         band_word<PAIR, TRACK>(a[2 * k + 1], x1, y1, maxsel_u);
       }
+    };
+    auto lds_cols = [&](const unsigned char* p, uint32_t (&w)[C]) {
+      if (C == 2) { const uint2 v = *reinterpret_cast<const uint2*>(p); w[0] = v.x; w[C - 1] = v.y; }
+      else { w[0] = *reinterpret_cast<const uint32_t*>(p); }
     };
 
     // shared-memory walk of this thread: pair q = slot, slot+nslots, ... ; pixel 2q sits at byte
@@ -269,17 +289,15 @@ fused_bip_kernel(FusedArgs g) {
         if (since_spill + steps > 127) {
           since_spill = 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) a[j].spill();
+          for (int j = 0; j < NB; ++j) a[j].spill();
         }
         since_spill += steps > 0 ? steps : 0;
         if (!MASK) n += steps > 0 ? 2 * steps : 0;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < steps; ++i) {
           const unsigned char* px = xs + (uint32_t)i * pstep;
-          const uint2 xa = *reinterpret_cast<const uint2*>(px);
-          const uint2 xb = *reinterpret_cast<const uint2*>(px + w4);
-          const uint2 ya = *reinterpret_cast<const uint2*>(px + cube_bytes);
-          const uint2 yb = *reinterpret_cast<const uint2*>(px + cube_bytes + w4);
+          uint32_t xa[C], xb[C], ya[C], yb[C];
+          lds_cols(px, xa); lds_cols(px + w4, xb); lds_cols(px + cube_bytes, ya); lds_cols(px + cube_bytes + w4, yb);
           uint32_t m = 0xffffffffu;
           if (MASK) {
             const int pa = 2 * (slot + i * nslots);
@@ -291,13 +309,13 @@ fused_bip_kernel(FusedArgs g) {
         if ((cnt & 1) && slot == 0) {                // odd leftover pixel of the tail tile
           const int pa = cnt - 1;
           const unsigned char* px = smem + (size_t)s * stage_bytes + ((size_t)pa * W + col) * 4;
-          const uint2 xa = *reinterpret_cast<const uint2*>(px);
-          const uint2 ya = *reinterpret_cast<const uint2*>(px + cube_bytes);
+          uint32_t xa[C], ya[C];
+          lds_cols(px, xa); lds_cols(px + cube_bytes, ya);
           uint32_t m = 0xffffffffu;
           if (MASK) m = (pl[pa] & DM_VALID_METRICS) ? 0xffffffffu : 0u;
           n += m ? 1 : 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) a[j].spill();
+          for (int j = 0; j < NB; ++j) a[j].spill();
           since_spill = 1;
           pair_step(xa, xa, ya, ya, m, std::false_type());
         }
@@ -306,22 +324,22 @@ fused_bip_kernel(FusedArgs g) {
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) a[j].spill();
+    for (int j = 0; j < NB; ++j) a[j].spill();
     if (!TRACK) maxsel_u = vmaxu2(umax, ymax);       // unmasked uint16: max over everything read
     // ---- combine the band group through shared memory (stage memory is free once every tile is done).
     // No atomics: every thread stores its 8 per-band values at [quantity][j][slot][column pair]
     // (consecutive lanes -> consecutive 8-byte words), then one thread per band adds the slots.
     asm volatile("bar.sync 1, %0;" ::"r"(kBandThreads + kPixelThreads));       // consumers only
-    unsigned long long* sh_part = reinterpret_cast<unsigned long long*>(smem);      // [8][4][nslots*tpp]
+    unsigned long long* sh_part = reinterpret_cast<unsigned long long*>(smem);      // [8][NB][nslots*tpp]
     const int lanes_used = nslots * tpp;
     __shared__ int sh_cube[8];
     if (ts < 8) sh_cube[ts] = ts == 2 ? 0x7fffffff : (ts == 0 ? (int)0x80000000 : 0);
     if (active) {
-      const int me = slot * tpp + (col >> 1);
+      const int me = slot * tpp + col / C;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NB; ++j) {
         unsigned long long* d = sh_part + (size_t)j * lanes_used + me;
-        const size_t q = (size_t)4 * lanes_used;
+        const size_t q = (size_t)NB * lanes_used;
         d[0 * q] = (unsigned long long)n;
         d[1 * q] = a[j].t_x; d[2 * q] = a[j].t_y; d[3 * q] = a[j].t_xx; d[4 * q] = a[j].t_yy; d[5 * q] = a[j].t_xy;
         d[6 * q] = a[j].t_abs; d[7 * q] = (unsigned long long)hmax2(a[j].maxd);
@@ -336,8 +354,8 @@ fused_bip_kernel(FusedArgs g) {
       sh_cube[4] = 1;
     }
     for (int b = ts; b < B; b += kBandThreads) {
-      const int cp = b >> 2, j = b & 3;
-      const size_t q = (size_t)4 * lanes_used;
+      const int cp = b / NB, j = b - cp * NB;
+      const size_t q = (size_t)NB * lanes_used;
       unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
       int md = 0;
       for (int sl = 0; sl < nslots; ++sl) {
@@ -508,6 +526,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
   g.want_sam = want_sam; g.spec_out = spectral_out;
+  { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
   const int sms = sm_count();
   if (sms < 0) return DM_ECUDA;
   const int64_t total = g.ntiles + (g.tail_pixels ? 1 : 0);
@@ -515,13 +534,22 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   size_t smem = (size_t)kStages * 2 * P * B * 2;
-  const size_t need_combine = (size_t)8 * 4 * kBandThreads * 8;   // [8][4][<=192] uint64 partials
+  const size_t need_combine = (size_t)8 * 2 * kMaxBandThreads * 8;   // [8][NB][<= band threads] uint64 partials
   if (smem < need_combine) smem = need_combine;
+  // C = 1 (twelve band warps, balanced schedulers) when one pixel needs at most 96 band threads per
+  // slot, i.e. up to 192 bands; C = 2 above that
+  const int cols = (B / 2 <= 96) ? 1 : 2;
 #define DM_FUSED(DT, MASK, ERR)                                                                       \
   do {                                                                                                \
-    auto k = fused_bip_kernel<DT, MASK, ERR>;                                                         \
-    DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    k<<<(unsigned)grid, kThreads, smem, s>>>(g);                                                      \
+    if (cols == 1) {                                                                                  \
+      auto k = fused_bip_kernel<DT, MASK, ERR, 1>;                                                    \
+      DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+      k<<<(unsigned)grid, Shape<1>::kThreads, smem, s>>>(g);                                          \
+    } else {                                                                                          \
+      auto k = fused_bip_kernel<DT, MASK, ERR, 2>;                                                    \
+      DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+      k<<<(unsigned)grid, Shape<2>::kThreads, smem, s>>>(g);                                          \
+    }                                                                                                 \
   } while (0)
   const bool err = errmax_out || err8_g || err8_z;
   if (p.dtype == DM_U16) {
