@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -49,11 +49,11 @@ SYMBOLS = {
     "dm_launch_count": (C.c_int64, []),
     "dm_validity": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P]),
     "dm_fused_stats": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
-    "dm_spectral_nblocks": (C.c_int, []),
+    "dm_workspace_bytes": (C.c_int64, []),
     "dm_spectral": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
-                              C.c_int32, C.c_int32, _P, _P]),
+                              C.c_int32, C.c_int32, _P, _P, _P]),
     "dm_fused_bip": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
-                               C.c_int32, _P, _P]),
+                               C.c_int32, _P, _P, _P]),
     "dm_sobel_nblocks": (C.c_int, []),
     "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_ssim_nblocks": (C.c_int, []),

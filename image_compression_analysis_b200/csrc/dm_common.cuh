@@ -29,20 +29,28 @@ void count_launch();                                // one more kernel launched 
 
 static inline int elem_bytes(int dtype) { return dtype == DM_U8 ? 1 : 2; }
 
+// Caller-provided device scratch (dm_workspace_bytes(), zeroed once by the caller): per-block float64
+// partials and the arrival counter of the in-kernel ordered final reduction.  The last block of a
+// launch resets the counter, so consecutive launches on one stream can share a workspace.
+constexpr int kMaxPartialBlocks = 1184;
+struct Workspace {
+  unsigned counter[16];
+  double part[3 * kMaxPartialBlocks];
+};
+
 // launchers implemented in the kernel translation units
 int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, int hist_bins,
                        uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, cudaStream_t s);
 int launch_validity(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out,
                     int64_t* counts, cudaStream_t s);
-int spectral_nblocks();
 int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_out,
                     const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
                     const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z,
-                    int want_sam, int want_sid, double* spectral_out, cudaStream_t s);
+                    int want_sam, int want_sid, double* spectral_acc, void* workspace, cudaStream_t s);
 int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
                      uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
                      const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
-                     double* spectral_out, cudaStream_t s);
+                     double* spectral_acc, void* workspace, cudaStream_t s);
 int sobel_nblocks();
 int ssim_nblocks();
 int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0,
@@ -145,6 +153,36 @@ __device__ __forceinline__ double block_sum_f64(double v, double* scratch) {
     v = warp_sum_f64(v);
   }
   return v;
+}
+
+// Ordered final reduction of per-block float64 partials {t0,t1,t2} (valid in lane 0).  Called by ONE
+// full warp of every block at the end of the kernel.  Each block stores its partials; the block that
+// arrives last adds them up in a fixed order (lane l takes blocks l, l+32, ...; then the shuffle tree)
+// and ACCUMULATES the result into acc[0..2], so the sum is bit-identical from run to run for a given
+// grid size, and a tail launch on the same stream composes with the main one.
+__device__ __forceinline__ void ordered_block_sum3(double t0, double t1, double t2, void* workspace, double* acc) {
+  Workspace* ws = static_cast<Workspace*>(workspace);
+  const int lane = threadIdx.x & 31;
+  unsigned last = 0;
+  if (lane == 0) {
+    double* d = ws->part + 3 * (size_t)blockIdx.x;
+    __stcg(d + 0, t0); __stcg(d + 1, t1); __stcg(d + 2, t2);
+    __threadfence();
+    last = atomicAdd(&ws->counter[0], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (unsigned i = lane; i < gridDim.x; i += 32) {
+    const double* d = ws->part + 3 * (size_t)i;
+    a0 += __ldcg(d + 0); a1 += __ldcg(d + 1); a2 += __ldcg(d + 2);
+  }
+  a0 = warp_sum_f64(a0); a1 = warp_sum_f64(a1); a2 = warp_sum_f64(a2);
+  if (lane == 0) {
+    acc[0] += a0; acc[1] += a1; acc[2] += a2;
+    ws->counter[0] = 0;
+  }
 }
 
 __device__ __forceinline__ void atomic_add_i64(int64_t* p, long long v) {

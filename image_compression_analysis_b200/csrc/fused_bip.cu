@@ -48,7 +48,6 @@ constexpr int kMaxBandThreads = 12 * 32;
 constexpr int kStages = 4;
 constexpr int kTilePixels = 64;                                  // pixels per tile (one half of the pixel group)
 constexpr int kStageBytesMax = 46080;                            // 2 cubes x 64 px x 180 bands x 2 B
-constexpr int kMaxSpecBlocks = 1184;                             // == dm_spectral_nblocks()
 
 struct FusedArgs {
   const void* ref;
@@ -65,8 +64,10 @@ struct FusedArgs {
   const uint8_t* lut_g; int cap_g; uint8_t* err8_g; int64_t* hist8_g;
   const uint8_t* lut_z; int cap_z; uint8_t* err8_z; int64_t* hist8_z;
   int want_sam;
-  int debug;                  // experiments only: 1 = producer skips the copies (compute-only timing)
-  double* spec_out;           // [3 * kMaxSpecBlocks]
+  int debug;                  // experiments only (DM_FUSED_DEBUG): 1 = producer skips the copies,
+                              // 2 = band group skips its arithmetic, 4 = pixel group skips its arithmetic
+  double* spec_acc;           // {sum arccos, -, n}, accumulated (ordered_block_sum3)
+  void* ws;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -85,17 +86,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ uint32_t vmaxu2(uint32_t a, uint32_t b) { uint32_t r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t vminu2(uint32_t a, uint32_t b) { uint32_t r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -105,8 +110,10 @@ __device__ __forceinline__ int hmin2(uint32_t p) { return min((int)(p & 0xffffu)
 __device__ __forceinline__ int hmax2s(uint32_t p) { return max((int)(short)(p & 0xffffu), (int)(short)(p >> 16)); }
 
 // per-band packed accumulators (same scheme as stats.cu)
-struct BandAcc {
+struct BandAccS {
   uint32_t sabs, sx, sy, xxl, xxh, yyl, yyh, xyl, xyh, maxd;
+};
+struct BandAcc : BandAccS {
   unsigned long long t_abs, t_x, t_y, t_xx, t_yy, t_xy;
   __device__ __forceinline__ void reset() {
     sabs = sx = sy = xxl = xxh = yyl = yyh = xyl = xyh = maxd = 0;
@@ -124,7 +131,7 @@ struct BandAcc {
 // TRACK: also fold max(x,y) into maxsel_u (the masked / int16 variants; the plain uint16 variant
 // takes the maxima of the natural words instead, two words per VIMNMX3)
 template <bool PAIR, bool TRACK>
-__device__ __forceinline__ void band_word(BandAcc& a, uint32_t x, uint32_t y, uint32_t& maxsel_u) {
+__device__ __forceinline__ void band_word(BandAccS& a, uint32_t x, uint32_t y, uint32_t& maxsel_u) {
   const uint32_t mx = vmaxu2(x, y), mn = vminu2(x, y), d = mx - mn;
   if (TRACK) maxsel_u = vmaxu2(maxsel_u, mx);
   a.maxd = vmaxu2(a.maxd, d);
@@ -483,14 +490,397 @@ fused_bip_kernel(FusedArgs g) {
     const int pw = warp - 1 - kBandWarps;
     if (lane == 0) { red[0][pw] = s_acos; red[2][pw] = s_n; }
     asm volatile("bar.sync 3, %0;" ::"r"(kPixelThreads));
-    if (tg == 0 && g.spec_out) {
+    if (tg < 32 && g.spec_acc) {
       double t0 = 0, t2 = 0;
       for (int w = 0; w < kPixelWarps; ++w) { t0 += red[0][w]; t2 += red[2][w]; }
-      g.spec_out[3 * blockIdx.x + 0] = t0; g.spec_out[3 * blockIdx.x + 1] = 0.0; g.spec_out[3 * blockIdx.x + 2] = t2;
+      ordered_block_sum3(t0, 0.0, t2, g.ws, g.spec_acc);
     }
-    if (blockIdx.x == 0 && g.spec_out)       // unused slots of the fixed-size partial array
-      for (int i = 3 * gridDim.x + tg; i < 3 * kMaxSpecBlocks; i += kPixelThreads) g.spec_out[i] = 0.0;
     for (int i = tg; i < 256; i += kPixelThreads) {
+      if (g.hist8_g && h8g[i]) atomic_add_i64(g.hist8_g + i, h8g[i]);
+      if (g.hist8_z && h8z[i]) atomic_add_i64(g.hist8_z + i, h8z[i]);
+    }
+  }
+}
+
+// =================================================================================================
+// Compile-time geometry variant (EnMAP: 180 bands).  Same band / pixel roles as the kernel above, but
+// there is no producer warp: the consumer warp that finishes a tile LAST (shared-memory arrival
+// counter) re-arms the stage's full barrier and issues the bulk copies of the tile four ahead.  Every
+// shared-memory offset is an immediate, a tile is always full (the launcher hands a partial last tile
+// to the generic kernel), band threads own FOUR bands (one LDS.64 per pixel and cube) and keep only
+// the 32-bit partials in registers: the rare spill (every 128 dp2a steps) goes to 64-bit
+// shared-memory totals, which also makes the end-of-kernel combine a plain per-band read.
+constexpr int kPixelWarpsCT = 8;
+constexpr int kPixelThreadsCT = kPixelWarpsCT * 32;
+template <int BANDS> struct Geo {
+  static constexpr int W = BANDS / 2;                   // 32-bit words per pixel
+  static constexpr int PIXB = BANDS * 2;                // bytes per pixel
+  static constexpr int P = kTilePixels;                 // 64
+  static constexpr int CUBE = P * PIXB;                 // one cube's share of a stage
+  static constexpr int STAGE = 2 * CUBE;
+  static constexpr int CHUNKS = BANDS / 4;              // 16-byte chunks per pixel pair
+  static constexpr int BAND_WARPS = (CHUNKS + 3) / 4, BAND_THREADS = BAND_WARPS * 32;   // 12 for 180 bands
+  static constexpr int ROWBLOCKS = P / 16;              // ldmatrix row blocks (8 pixel pairs) per tile
+  static constexpr int THREADS = BAND_THREADS + kPixelThreadsCT;   // 640: 20 warps x 96 registers
+  static constexpr int CONSUMERS = BAND_WARPS + kPixelWarpsCT / 2;    // warps that read one tile
+  static constexpr int NQ = 6;                          // abs, x, y, xx, yy, xy
+  static constexpr size_t TOT_BYTES = (size_t)(NQ + 1) * BANDS * 8 + (size_t)BANDS * 4;   // totals, N, max|d|
+  static constexpr size_t SMEM = (size_t)kStages * STAGE + TOT_BYTES;
+  static_assert(BANDS % 4 == 0 && BANDS <= 256, "dp2a lo/hi pixel partials need B <= 256");
+  static_assert(SMEM <= 227 * 1024, "ring does not fit");
+  static_assert((PIXB / 8) % 2 == 1, "conflict-free LDS.64 / ldmatrix walks need an odd pixel pitch in 8-byte units");
+  static_assert(BAND_WARPS == 12, "the 20-warp layout (3 band + 2 pixel warps per scheduler) assumes 12 band warps");
+};
+
+// barrier helpers on raw shared-memory addresses (computed once per thread, not per tile)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+// arrive and tell whether this was the LAST pending arrival of the phase (exactly one arriver sees it)
+__device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
+  uint64_t st;
+  uint32_t pending;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(st));
+  return pending == 1u;
+}
+
+template <int BANDS, int DT, bool MASK, bool ERR>
+__global__ void __launch_bounds__(Geo<BANDS>::THREADS, 1)
+fused_ct_kernel(FusedArgs g) {
+  using G = Geo<BANDS>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ unsigned h8g[256], h8z[256];
+  __shared__ double red[3][kPixelWarpsCT];
+  __shared__ int sh_cube[8];
+  unsigned long long* tot = reinterpret_cast<unsigned long long*>(smem + (size_t)kStages * G::STAGE);   // [NQ][BANDS]
+  unsigned long long* tot_n = tot + G::NQ * BANDS;                                                      // [BANDS]
+  unsigned* tot_maxd = reinterpret_cast<unsigned*>(tot_n + BANDS);                                      // [BANDS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t OFS = DT == DM_I16 ? 0x80008000u : 0u;
+  constexpr bool TRACK = MASK || DT == DM_I16;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], G::CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 256) { h8g[tid] = 0; h8z[tid] = 0; }
+  if (tid < 8) sh_cube[tid] = tid == 2 ? 0x7fffffff : (tid == 0 ? (int)0x80000000 : 0);
+  for (int i = tid; i < (G::NQ + 1) * BANDS; i += G::THREADS) tot[i] = 0ull;
+  for (int i = tid; i < BANDS; i += G::THREADS) tot_maxd[i] = 0u;
+  __syncthreads();
+
+  // tiles of this CTA: local index it = 0 .. my_tiles-1 is global tile blockIdx.x + it*gridDim.x and
+  // lives in stage it % kStages (full tiles only; the launcher hands a partial tile to the generic kernel)
+  const int my_tiles = (int64_t)blockIdx.x < g.ntiles ? (int)((g.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const int dbg = g.debug;
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+
+  auto issue_tile = [&](int it) {
+    if (it >= my_tiles) return;
+    const int s = it & (kStages - 1);
+    uint64_t* fb = &full_bar[s];
+    if (dbg & 1) { mbar_arrive(fb); return; }
+    const int64_t off = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)G::CUBE;
+    unsigned char* dst = smem + (size_t)s * G::STAGE;
+    mbar_expect_tx(fb, G::STAGE);
+    bulk_g2s(dst, static_cast<const char*>(g.ref) + off, G::CUBE, fb);
+    bulk_g2s(dst + G::CUBE, static_cast<const char*>(g.tst) + off, G::CUBE, fb);
+  };
+  // Called by lane 0 of a consumer warp when the warp has finished reading tile `it`.  There is no
+  // producer warp: every consumer warp arrives on the stage's empty barrier, and the one whose arrival
+  // completes the phase (the last of the CONSUMERS warps) refills the stage with tile it + kStages.
+  // The (immediately successful) wait on the completed phase gives that thread acquire ordering on
+  // the other warps' shared-memory reads before the asynchronous proxy overwrites the stage.
+  auto release_tile = [&](int it) {
+    const uint32_t eb = empty0 + 8u * (uint32_t)(it & (kStages - 1));
+    if (mbar_arrive_is_last_a(eb)) {
+      mbar_wait_a(eb, (uint32_t)((it / kStages) & 1));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_tile(it + kStages);
+    }
+  };
+  if (tid == 0) {
+    for (int it = 0; it < kStages; ++it) issue_tile(it);
+  }
+
+  if (warp < G::BAND_WARPS) {
+    // ------------------------------------------------------------------ band group
+    // A pixel PAIR (even pixel, odd pixel) is 2*PIXB bytes = CHUNKS 16-byte chunks, and 16-bit column c
+    // of chunk k is always the same (pixel parity, band): sample column sc = 8k + c, parity sc / BANDS,
+    // band sc % BANDS.  ldmatrix.trans over 8 pixel-pair rows x one chunk hands thread (c = lane/4,
+    // r = lane%4) the word [row 2r+1 | row 2r] of column c -- two pixels of the SAME band, which is the
+    // operand pairing dp2a needs, with no PRMT regrouping.  Warp w owns chunks 4w .. 4w+3 (x4: four
+    // chunks per instruction), i.e. four fixed sample columns per thread, accumulated in registers.
+    // Row addresses are 2*PIXB apart = 45 chunks, odd, so the eight rows of a matrix hit eight
+    // different 16-byte bank groups (conflict free).
+    const int ts = tid;
+    const int c = lane >> 2, r = lane & 3;
+    const int nmat = (G::CHUNKS - 4 * warp) < 4 ? (G::CHUNKS - 4 * warp) : 4;     // >= 1 for every band warp
+    const int sc0 = 32 * warp + c;                     // sample column of matrix j: sc0 + 8j
+    auto par_of = [&](int j) { return sc0 + 8 * j >= BANDS; };
+    auto band_of = [&](int j) { const int sc = sc0 + 8 * j; return sc >= BANDS ? sc - BANDS : sc; };
+    const int mchunk = (4 * warp + (lane >> 3)) < G::CHUNKS ? (4 * warp + (lane >> 3)) : (G::CHUNKS - 1);
+    const uint32_t ld_off = ring + (uint32_t)(lane & 7) * (2u * G::PIXB) + (uint32_t)mchunk * 16u;
+    BandAccS a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; }
+    uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
+    uint32_t n0 = 0, n1 = 0;                           // MASK: selected even / odd pixels of this thread's rows
+
+    auto spill = [&]() {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nmat) {
+          const int b = band_of(j);
+          atomicAdd(tot + 0 * BANDS + b, (unsigned long long)a[j].sabs);
+          atomicAdd(tot + 1 * BANDS + b, (unsigned long long)a[j].sx);
+          atomicAdd(tot + 2 * BANDS + b, (unsigned long long)a[j].sy);
+          atomicAdd(tot + 3 * BANDS + b, (unsigned long long)a[j].xxl + ((unsigned long long)a[j].xxh << 8));
+          atomicAdd(tot + 4 * BANDS + b, (unsigned long long)a[j].yyl + ((unsigned long long)a[j].yyh << 8));
+          atomicAdd(tot + 5 * BANDS + b, (unsigned long long)a[j].xyl + ((unsigned long long)a[j].xyh << 8));
+        }
+        a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = 0;
+      }
+    };
+
+    // NM = matrices (chunks) this warp really owns: 4, or fewer in the last band warp; a compile-time
+    // count keeps the row block free of branches so that the four columns interleave.  Tiles run in
+    // epochs of 128 / ROWBLOCKS: a 32-bit partial takes one dp2a per row block and holds 128 of them
+    // (2 * 65535 * 255 each), so the spill to the 64-bit shared totals sits outside the tile loop.
+    auto run = [&](auto nm_tag) {
+      constexpr int NM = decltype(nm_tag)::value;
+      constexpr int EPOCH = 128 / G::ROWBLOCKS;
+      for (int it0 = 0; it0 < my_tiles; it0 += EPOCH) {
+        const int it1 = it0 + EPOCH < my_tiles ? it0 + EPOCH : my_tiles;
+        for (int it = it0; it < it1; ++it) {
+          const int s = it & (kStages - 1);
+          mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1));
+          if (!(dbg & 2)) {
+            const uint32_t xs = ld_off + (uint32_t)s * G::STAGE;
+            const uint8_t* pl = MASK ? g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P : nullptr;
+#pragma unroll
+            for (int rb = 0; rb < G::ROWBLOCKS; ++rb) {
+              uint32_t xr[4], yr[4];
+              ldsm_x4_trans(xr, xs + rb * (16 * G::PIXB));
+              ldsm_x4_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+              uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+              if (MASK) {
+                // pixels 16rb + 4r .. +3 of the tile: even/odd pixel of row 2r, even/odd pixel of row 2r+1
+                const uint32_t vb = *reinterpret_cast<const uint32_t*>(pl + 16 * rb + 4 * r);
+                m0 = ((vb & DM_VALID_METRICS) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 16)) ? 0xffff0000u : 0u);
+                m1 = ((vb & (DM_VALID_METRICS << 8)) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 24)) ? 0xffff0000u : 0u);
+                n0 += (m0 & 1u) + (m0 >> 31);
+                n1 += (m1 & 1u) + (m1 >> 31);
+              }
+              // data-range scan on the raw reference words (unmasked); a short last warp re-reads its
+              // last chunk in the unused matrices, which changes neither an OR nor a maximum
+              orbits |= xr[0] | xr[1]; orbits |= xr[2] | xr[3];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { xr[j] ^= OFS; yr[j] ^= OFS; }
+              umax = __vimax3_u16x2(umax, xr[0], xr[1]); umax = __vimax3_u16x2(umax, xr[2], xr[3]);
+              if (DT == DM_I16) { umin = __vimin3_u16x2(umin, xr[0], xr[1]); umin = __vimin3_u16x2(umin, xr[2], xr[3]); }
+              if (!TRACK) { ymax = __vimax3_u16x2(ymax, yr[0], yr[1]); ymax = __vimax3_u16x2(ymax, yr[2], yr[3]); }
+#pragma unroll
+              for (int j = 0; j < NM; ++j) {
+                uint32_t x = xr[j], y = yr[j];
+                if (MASK) { const uint32_t m = par_of(j) ? m1 : m0; x &= m; y &= m; }
+                if (DT == DM_I16) {
+                  // np.abs semantics on the signed samples (wrapping abs of -32768 never wins)
+                  const uint32_t mm = MASK ? (par_of(j) ? m1 : m0) : 0xffffffffu;
+                  maxsel_s = __vimax3_s16x2(maxsel_s, __vabs2((x ^ OFS) & mm), __vabs2((y ^ OFS) & mm));
+                }
+                band_word<true, TRACK>(a[j], x, y, maxsel_u);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) release_tile(it);
+        }
+        spill();
+      }
+    };
+    if (nmat == 4) run(std::integral_constant<int, 4>());
+    else if (nmat == 3) run(std::integral_constant<int, 3>());
+    else if (nmat == 2) run(std::integral_constant<int, 2>());
+    else run(std::integral_constant<int, 1>());
+
+    // ---- flush: per-band maxima and counts -> shared, then one thread per band -> global
+    if (my_tiles > 0 && !(dbg & 2)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nmat) {
+          atomicMax(tot_maxd + band_of(j), (unsigned)hmax2(a[j].maxd));
+          if (MASK) atomicAdd(tot_n + band_of(j), (unsigned long long)(par_of(j) ? n1 : n0));
+        }
+      }
+      if (!TRACK) maxsel_u = vmaxu2(umax, ymax);       // unmasked uint16: max over everything read
+      atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(maxsel_s) : hmax2(maxsel_u));
+      atomicMax(sh_cube + 1, hmax2(umax));
+      atomicMin(sh_cube + 2, hmin2(umin));
+      atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (orbits | (orbits >> 16)) & 0xffffu);
+      sh_cube[4] = 1;
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"(G::BAND_THREADS));
+    const long long n_cta = (dbg & 2) ? 0 : (long long)my_tiles * G::P;      // pixels this CTA has read
+    for (int b = ts; b < BANDS; b += G::BAND_THREADS) {
+      long long nn = MASK ? (long long)tot_n[b] : n_cta;
+      long long sab = (long long)tot[0 * BANDS + b], sx = (long long)tot[1 * BANDS + b], sy = (long long)tot[2 * BANDS + b];
+      long long sxx = (long long)tot[3 * BANDS + b], syy = (long long)tot[4 * BANDS + b], sxy = (long long)tot[5 * BANDS + b];
+      const int md = (int)tot_maxd[b];
+      if (DT == DM_I16) {
+        const long long c = 32768, c2 = 32768ll * 32768ll;
+        const long long xx = sxx - 2 * c * sx + c2 * nn, yy = syy - 2 * c * sy + c2 * nn;
+        const long long xy = sxy - c * (sx + sy) + c2 * nn;
+        sx -= c * nn; sy -= c * nn; sxx = xx; syy = yy; sxy = xy;
+      }
+      int64_t* O = g.sums + (int64_t)b * DM_NSTAT;
+      if (nn) atomic_add_i64(O + DM_S_N, nn);
+      if (sab) atomic_add_i64(O + DM_S_ABS, sab);
+      if (sx) atomic_add_i64(O + DM_S_X, sx);
+      if (sy) atomic_add_i64(O + DM_S_Y, sy);
+      if (sxx) atomic_add_i64(O + DM_S_XX, sxx);
+      if (syy) atomic_add_i64(O + DM_S_YY, syy);
+      if (sxy) atomic_add_i64(O + DM_S_XY, sxy);
+      const long long sse = sxx + syy - 2 * sxy;
+      if (sse) atomic_add_i64(O + DM_S_SSE, sse);
+      if (md) atomic_max_i64(g.maxs + (int64_t)b * DM_NSTAT + DM_M_MAXERR, md);
+    }
+    if (ts == 0 && sh_cube[4]) {
+      int64_t* M = g.maxs;
+      if (DT == DM_I16) {
+        const int hi = sh_cube[1] - 32768, lo = sh_cube[2] - 32768;
+        if (hi > 0) atomic_max_i64(M + DM_M_UMAX, hi);
+        if (lo < 0) atomic_max_i64(M + DM_M_UNEGMIN, -lo);
+      } else if (sh_cube[1] > 0) {
+        atomic_max_i64(M + DM_M_UMAX, sh_cube[1]);
+      }
+      if (sh_cube[0] > 0) atomic_max_i64(M + DM_M_ABSXY, sh_cube[0]);
+      if (sh_cube[3] & 0xF) atomic_max_i64(M + DM_M_LOW4, 1);
+      if (sh_cube[3] & 0x3) atomic_max_i64(M + DM_M_LOW2, 1);
+    }
+  } else {
+    // ------------------------------------------------------------------ pixel group
+    // Two 4-warp groups take alternate tiles; inside a group TWO lanes share a pixel (lane l and
+    // l+16 walk the two halves of its spectrum), which halves the time a stage is held.  The halves
+    // are combined with one shuffle per partial; the float64 finish is batched over two visits
+    // (lanes 0-15 keep the pixels of the even visit, lanes 16-31 those of the odd one) so that all
+    // 32 lanes of the warp work in it.
+    const int tg = tid - G::BAND_THREADS;             // 0..255
+    const int grp = tg >> 7;                          // tile parity this group serves
+    const int wq = (tg >> 5) & 3;                     // warp of the group: pixels 16wq .. 16wq+15
+    const int hl = lane >> 4;                         // half of the spectrum this lane walks
+    const int tp = 16 * wq + (lane & 15);
+    constexpr int U = G::W / 2;                       // 8-byte units per pixel
+    constexpr int H0 = (U + 1) / 2, H1 = U - H0;      // units of half 0 / half 1
+    const unsigned char* lane_base = smem + (size_t)tp * G::PIXB + (hl ? H0 * 8 : 0);
+    double s_acos = 0.0, s_n = 0.0;
+    uint32_t k_xxl = 0, k_xxh = 0, k_yyl = 0, k_yyh = 0, k_xyl = 0, k_xyh = 0, k_sx = 0, k_sy = 0, k_e = 0;
+    int k_it = 0;
+
+    auto finish = [&]() {
+      const int64_t p = ((int64_t)blockIdx.x + (int64_t)k_it * gridDim.x) * G::P + tp;
+      const uint8_t v = MASK ? g.plane[p] : (uint8_t)0xff;
+      if (ERR) {
+        int e = (v & DM_VALID_QUICKLOOK) ? hmax2(k_e) : 0;             // quicklooks.py:134
+        if (g.errmax) g.errmax[p] = (uint16_t)e;
+        if (g.err8_g) {
+          const uint8_t e8 = __ldg(g.lut_g + min(e, g.cap_g));
+          g.err8_g[p] = e8;
+          if (g.hist8_g) hist_add(h8g, e8);
+        }
+        if (g.err8_z) {
+          const uint8_t e8 = __ldg(g.lut_z + min(e, g.cap_z));
+          g.err8_z[p] = e8;
+          if (g.hist8_z) hist_add(h8z, e8);
+        }
+      }
+      if (g.want_sam && (v & DM_VALID_SPECTRAL)) {
+        // lo + 256*hi: both halves < 2^32 and the sum < 2^53, so float64 holds it exactly
+        double na2 = fma((double)k_xxh, 256.0, (double)k_xxl);
+        double nr2 = fma((double)k_yyh, 256.0, (double)k_yyl);
+        double dot = fma((double)k_xyh, 256.0, (double)k_xyl);
+        if (DT == DM_I16) {
+          const double c = 32768.0, c2B = 32768.0 * 32768.0 * (double)BANDS, fx = (double)k_sx, fy = (double)k_sy;
+          dot = dot - c * (fx + fy) + c2B;             // all terms exact integers below 2^53
+          na2 = na2 - 2.0 * c * fx + c2B;
+          nr2 = nr2 - 2.0 * c * fy + c2B;
+        }
+        const double na = __dadd_rn(__dsqrt_rn(na2), 1e-12);
+        const double nr = __dadd_rn(__dsqrt_rn(nr2), 1e-12);
+        double c = __ddiv_rn(dot, __dmul_rn(na, nr));
+        c = fmin(1.0, fmax(-1.0, c));
+        s_acos += acos_sam(c);
+        s_n += 1.0;
+      }
+    };
+
+    int visit = 0;
+    for (int it = grp; it < my_tiles; it += 2, ++visit) {
+      const int s = it & (kStages - 1);
+      mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1));
+      uint32_t emax = 0;
+      uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0, sx = 0, sy = 0;
+      if (!(dbg & 4)) {
+        const unsigned char* xs = lane_base + (size_t)s * G::STAGE;
+        auto unit = [&](int j) {
+          const uint2 xv = *reinterpret_cast<const uint2*>(xs + 8 * j);
+          const uint2 yv = *reinterpret_cast<const uint2*>(xs + G::CUBE + 8 * j);
+          const uint32_t xw[2] = {xv.x ^ OFS, xv.y ^ OFS}, yw[2] = {yv.x ^ OFS, yv.y ^ OFS};
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t x = xw[k], y = yw[k];
+            if (ERR) emax = vmaxu2(emax, vmaxu2(x, y) - vminu2(x, y));
+            const uint32_t px = __byte_perm(x, 0, 0x3120), py = __byte_perm(y, 0, 0x3120);
+            xxl = dp2a_lo(x, px, xxl); xxh = dp2a_hi(x, px, xxh);
+            yyl = dp2a_lo(y, py, yyl); yyh = dp2a_hi(y, py, yyh);
+            xyl = dp2a_lo(x, py, xyl); xyh = dp2a_hi(x, py, xyh);
+            if (DT == DM_I16) { sx = dp2a_lo(x, 0x0101u, sx); sy = dp2a_lo(y, 0x0101u, sy); }
+          }
+        };
+#pragma unroll 11
+        for (int j = 0; j < H1; ++j) unit(j);
+        if (H0 > H1 && hl == 0) unit(H1);              // the odd unit belongs to half 0
+      }
+      // the stage is no longer needed: release it before the shuffles and the float64 work
+      __syncwarp();
+      if (lane == 0) release_tile(it);
+      if (!(dbg & 4)) {
+        xxl += __shfl_xor_sync(0xffffffffu, xxl, 16); xxh += __shfl_xor_sync(0xffffffffu, xxh, 16);
+        yyl += __shfl_xor_sync(0xffffffffu, yyl, 16); yyh += __shfl_xor_sync(0xffffffffu, yyh, 16);
+        xyl += __shfl_xor_sync(0xffffffffu, xyl, 16); xyh += __shfl_xor_sync(0xffffffffu, xyh, 16);
+        if (DT == DM_I16) { sx += __shfl_xor_sync(0xffffffffu, sx, 16); sy += __shfl_xor_sync(0xffffffffu, sy, 16); }
+        if (ERR) emax = vmaxu2(emax, __shfl_xor_sync(0xffffffffu, emax, 16));
+        if (hl == (visit & 1)) {
+          k_xxl = xxl; k_xxh = xxh; k_yyl = yyl; k_yyh = yyh; k_xyl = xyl; k_xyh = xyh; k_sx = sx; k_sy = sy; k_e = emax;
+          k_it = it;
+        }
+        if (visit & 1) finish();
+      }
+    }
+    if ((visit & 1) && hl == 0 && !(dbg & 4)) finish();      // pixels of an unpaired last visit
+    __syncwarp();
+    s_acos = warp_sum_f64(s_acos); s_n = warp_sum_f64(s_n);
+    const int pw = warp - G::BAND_WARPS;
+    if (lane == 0) { red[0][pw] = s_acos; red[2][pw] = s_n; }
+    asm volatile("bar.sync 3, %0;" ::"r"(kPixelThreadsCT));
+    if (tg < 32 && g.spec_acc) {
+      double t0 = 0, t2 = 0;
+      for (int w = 0; w < kPixelWarpsCT; ++w) { t0 += red[0][w]; t2 += red[2][w]; }
+      ordered_block_sum3(t0, 0.0, t2, g.ws, g.spec_acc);
+    }
+    for (int i = tg; i < 256; i += kPixelThreadsCT) {
       if (g.hist8_g && h8g[i]) atomic_add_i64(g.hist8_g + i, h8g[i]);
       if (g.hist8_z && h8z[i]) atomic_add_i64(g.hist8_z + i, h8z[i]);
     }
@@ -499,38 +889,20 @@ fused_bip_kernel(FusedArgs g) {
 
 }  // namespace
 
-int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
-                     uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
-                     const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
-                     double* spectral_out, cudaStream_t s) {
-  if (!p.ref || !p.tst || !sums || !maxs) return fail(DM_EARG, "dm_fused_bip: null pointer");
-  if (p.layout != DM_BIP) return fail(DM_EUNSUPPORTED, "dm_fused_bip: BIP cubes only");
-  if (p.dtype != DM_U16 && p.dtype != DM_I16) return fail(DM_EUNSUPPORTED, "dm_fused_bip: 16-bit samples only");
-  const int64_t B = p.bands;
-  // dp2a lo/hi partials of one pixel stay below 2^32 up to 256 bands; 4 <= B, B % 4 == 0 for the
-  // 8-byte column pairs; at most 192 band-group threads per pixel slot
-  if (B < 4 || B % 4 || B > 256) return fail(DM_EUNSUPPORTED, "dm_fused_bip: bands must be a multiple of 4 in 4..256");
-  if ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 15)
-    return fail(DM_EUNSUPPORTED, "dm_fused_bip: cubes must be 16-byte aligned");
-  if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_fused_bip: bad global LUT");
-  if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_fused_bip: bad zoom LUT");
-  if (want_sam && !spectral_out) return fail(DM_EARG, "dm_fused_bip: spectral_out is null");
-  FusedArgs g;
-  g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
+namespace {
+
+// generic kernel over g.npix pixels (full tiles by TMA, one partial tile by plain loads)
+int run_generic(FusedArgs g, int dtype, cudaStream_t s) {
+  const int64_t B = g.bands;
   int P = kTilePixels;                                 // 64 pixels per tile when they fit a stage
   while ((int64_t)P * B * 4 > kStageBytesMax) P >>= 1;
   g.P = P;                                             // P*B*2 is a multiple of 16 (P even, B % 4 == 0)
   g.ntiles = g.npix / P;
   g.tail_pixels = (int)(g.npix - g.ntiles * P);
-  g.sums = sums; g.maxs = maxs; g.errmax = errmax_out;
-  g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
-  g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
-  g.want_sam = want_sam; g.spec_out = spectral_out;
-  { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
   const int sms = sm_count();
   if (sms < 0) return DM_ECUDA;
   const int64_t total = g.ntiles + (g.tail_pixels ? 1 : 0);
-  int64_t grid = sms < kMaxSpecBlocks ? sms : kMaxSpecBlocks;
+  int64_t grid = sms < kMaxPartialBlocks ? sms : kMaxPartialBlocks;
   if (grid > total) grid = total;
   if (grid < 1) grid = 1;
   size_t smem = (size_t)kStages * 2 * P * B * 2;
@@ -551,17 +923,90 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
       k<<<(unsigned)grid, Shape<2>::kThreads, smem, s>>>(g);                                          \
     }                                                                                                 \
   } while (0)
-  const bool err = errmax_out || err8_g || err8_z;
-  if (p.dtype == DM_U16) {
-    if (plane) { if (err) DM_FUSED(DM_U16, true, true); else DM_FUSED(DM_U16, true, false); }
+  const bool err = g.errmax || g.err8_g || g.err8_z;
+  if (dtype == DM_U16) {
+    if (g.plane) { if (err) DM_FUSED(DM_U16, true, true); else DM_FUSED(DM_U16, true, false); }
     else { if (err) DM_FUSED(DM_U16, false, true); else DM_FUSED(DM_U16, false, false); }
   } else {
-    if (plane) { if (err) DM_FUSED(DM_I16, true, true); else DM_FUSED(DM_I16, true, false); }
+    if (g.plane) { if (err) DM_FUSED(DM_I16, true, true); else DM_FUSED(DM_I16, true, false); }
     else { if (err) DM_FUSED(DM_I16, false, true); else DM_FUSED(DM_I16, false, false); }
   }
 #undef DM_FUSED
   DM_LAUNCH_CHECK("fused_bip");
   return DM_OK;
+}
+
+// compile-time geometry kernel over g.ntiles FULL tiles of 64 pixels
+template <int BANDS>
+int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
+  using G = Geo<BANDS>;
+  g.P = G::P; g.tail_pixels = 0;
+  const int sms = sm_count();
+  if (sms < 0) return DM_ECUDA;
+  int64_t grid = sms < kMaxPartialBlocks ? sms : kMaxPartialBlocks;
+  if (grid > g.ntiles) grid = g.ntiles;
+#define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
+  do {                                                                                                \
+    auto k = fused_ct_kernel<BANDS, DT, MASK, ERR>;                                                   \
+    DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));      \
+    k<<<(unsigned)grid, G::THREADS, G::SMEM, s>>>(g);                                                 \
+  } while (0)
+  const bool err = g.errmax || g.err8_g || g.err8_z;
+  if (dtype == DM_U16) {
+    if (g.plane) { if (err) DM_FUSED_CT(DM_U16, true, true); else DM_FUSED_CT(DM_U16, true, false); }
+    else { if (err) DM_FUSED_CT(DM_U16, false, true); else DM_FUSED_CT(DM_U16, false, false); }
+  } else {
+    if (g.plane) { if (err) DM_FUSED_CT(DM_I16, true, true); else DM_FUSED_CT(DM_I16, true, false); }
+    else { if (err) DM_FUSED_CT(DM_I16, false, true); else DM_FUSED_CT(DM_I16, false, false); }
+  }
+#undef DM_FUSED_CT
+  DM_LAUNCH_CHECK("fused_bip_ct");
+  return DM_OK;
+}
+
+}  // namespace
+
+int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
+                     uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                     const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
+                     double* spectral_acc, void* workspace, cudaStream_t s) {
+  if (!p.ref || !p.tst || !sums || !maxs) return fail(DM_EARG, "dm_fused_bip: null pointer");
+  if (p.layout != DM_BIP) return fail(DM_EUNSUPPORTED, "dm_fused_bip: BIP cubes only");
+  if (p.dtype != DM_U16 && p.dtype != DM_I16) return fail(DM_EUNSUPPORTED, "dm_fused_bip: 16-bit samples only");
+  const int64_t B = p.bands;
+  // dp2a lo/hi partials of one pixel stay below 2^32 up to 256 bands; 4 <= B, B % 4 == 0 for the
+  // 8-byte column pairs; at most 192 band-group threads per pixel slot
+  if (B < 4 || B % 4 || B > 256) return fail(DM_EUNSUPPORTED, "dm_fused_bip: bands must be a multiple of 4 in 4..256");
+  if ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 15)
+    return fail(DM_EUNSUPPORTED, "dm_fused_bip: cubes must be 16-byte aligned");
+  if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_fused_bip: bad global LUT");
+  if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_fused_bip: bad zoom LUT");
+  if (want_sam && (!spectral_acc || !workspace)) return fail(DM_EARG, "dm_fused_bip: spectral_acc / workspace is null");
+  FusedArgs g;
+  g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
+  g.P = 0; g.ntiles = 0; g.tail_pixels = 0;
+  g.sums = sums; g.maxs = maxs; g.errmax = errmax_out;
+  g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
+  g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
+  g.want_sam = want_sam; g.spec_acc = want_sam ? spectral_acc : nullptr; g.ws = workspace;
+  { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  if (g.npix <= 0) return DM_OK;
+  const bool force_generic = (g.debug & 8) != 0;
+  if (B == 180 && g.npix >= kTilePixels && !force_generic) {
+    // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
+    g.ntiles = g.npix / kTilePixels;
+    const int64_t done = g.ntiles * kTilePixels;
+    int rc = run_ct<180>(g, p.dtype, s);
+    if (rc != DM_OK || done == g.npix) return rc;
+    g.ref = static_cast<const char*>(g.ref) + done * B * 2;
+    g.tst = static_cast<const char*>(g.tst) + done * B * 2;
+    if (g.plane) g.plane += done;
+    if (g.errmax) g.errmax += done;
+    if (g.err8_g) g.err8_g += done;
+    if (g.err8_z) g.err8_z += done;
+    g.npix -= done;
+  }
+  return run_generic(g, p.dtype, s);
 }
 
 }  // namespace dm

@@ -63,24 +63,24 @@ int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, 
                             static_cast<cudaStream_t>(stream));
 }
 
-int dm_spectral_nblocks(void) { return spectral_nblocks(); }
+int64_t dm_workspace_bytes(void) { return (int64_t)sizeof(Workspace); }
 
 int dm_spectral(const dm_pair_t* p, const uint8_t* plane, uint16_t* errmax_out, const uint8_t* lut_g,
                 int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z, int32_t cap_z,
                 uint8_t* err8_z, int64_t* hist8_z, int32_t want_sam, int32_t want_sid,
-                double* spectral_out, void* stream) {
+                double* spectral_acc, void* workspace, void* stream) {
   if (!p) return fail(DM_EARG, "dm_spectral: null pair");
   return launch_spectral(*p, plane, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
-                         hist8_z, want_sam, want_sid, spectral_out, static_cast<cudaStream_t>(stream));
+                         hist8_z, want_sam, want_sid, spectral_acc, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z,
-                 int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, int32_t want_sam, double* spectral_out,
-                 void* stream) {
+                 int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, int32_t want_sam, double* spectral_acc,
+                 void* workspace, void* stream) {
   if (!p) return fail(DM_EARG, "dm_fused_bip: null pair");
   return launch_fused_bip(*p, plane, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
-                          hist8_z, want_sam, spectral_out, static_cast<cudaStream_t>(stream));
+                          hist8_z, want_sam, spectral_acc, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int dm_sobel_nblocks(void) { return sobel_nblocks(); }

@@ -7,7 +7,8 @@
 // SAM's dot / |a|^2 / |r|^2 are exact int64 sums (<= 180*65535^2 < 2^53), so cos(angle) is
 // reproduced bit-for-bit with correctly rounded sqrt / mul / div; acos and log are libdevice
 // (<= 2 ulp).  SID follows the reference's float64 expressions term by term.  Floating-point
-// partial sums are written per block in block order so that the host reduction is deterministic.
+// partial sums are combined in a fixed order by the last block of the launch (ordered_block_sum3)
+// and accumulated into the caller's {sum arccos, sum sid, n}.
 //
 // The ERR8 scaling is a float32 chain in the reference (clip((e-0)/(cap+1e-9),0,1)*255 -> uint8);
 // the host tabulates it with the reference's own expression for e = 0..cap and the kernel only
@@ -19,7 +20,7 @@ namespace dm {
 
 namespace {
 
-constexpr int kSpecBlocks = 1184;     // fixed: the per-block partial layout must not depend on the device
+constexpr int kSpecBlocks = kMaxPartialBlocks;   // fixed grid: the summation order must not depend on the device
 constexpr int kSpecThreads = 256;
 
 struct SpecArgs {
@@ -32,7 +33,8 @@ struct SpecArgs {
   const uint8_t* lut_g; int cap_g; uint8_t* err8_g; int64_t* hist8_g;
   const uint8_t* lut_z; int cap_z; uint8_t* err8_z; int64_t* hist8_z;
   int want_sam, want_sid;
-  double* out;
+  double* acc;                // {sum arccos, sum sid, n}, accumulated
+  void* ws;
 };
 
 template <typename T>
@@ -111,10 +113,10 @@ spectral_pixel(SpecArgs g) {
   s_acos = warp_sum_f64(s_acos); s_sid = warp_sum_f64(s_sid); s_n = warp_sum_f64(s_n);
   if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
   __syncthreads();
-  if (tid == 0 && g.out) {
+  if (tid < 32 && g.acc) {
     double t0 = 0, t1 = 0, t2 = 0;
     for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
-    g.out[3 * blockIdx.x + 0] = t0; g.out[3 * blockIdx.x + 1] = t1; g.out[3 * blockIdx.x + 2] = t2;
+    ordered_block_sum3(t0, t1, t2, g.ws, g.acc);
   }
   if (g.hist8_g && hg[tid]) atomic_add_i64(g.hist8_g + tid, hg[tid]);
   if (g.hist8_z && hz[tid]) atomic_add_i64(g.hist8_z + tid, hz[tid]);
@@ -198,10 +200,10 @@ spectral_warp_bip(SpecArgs g) {
   }
   if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
   __syncthreads();
-  if (tid == 0 && g.out) {
+  if (tid < 32 && g.acc) {
     double t0 = 0, t1 = 0, t2 = 0;
     for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
-    g.out[3 * blockIdx.x + 0] = t0; g.out[3 * blockIdx.x + 1] = t1; g.out[3 * blockIdx.x + 2] = t2;
+    ordered_block_sum3(t0, t1, t2, g.ws, g.acc);
   }
   if (g.hist8_g && hg[tid]) atomic_add_i64(g.hist8_g + tid, hg[tid]);
   if (g.hist8_z && hz[tid]) atomic_add_i64(g.hist8_z + tid, hz[tid]);
@@ -219,18 +221,17 @@ int run_spectral(const SpecArgs& g, bool bip, cudaStream_t s) {
 
 }  // namespace
 
-int spectral_nblocks() { return kSpecBlocks; }
-
 int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_out, const uint8_t* lut_g,
                     int cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z, int cap_z,
-                    uint8_t* err8_z, int64_t* hist8_z, int want_sam, int want_sid, double* spectral_out,
-                    cudaStream_t s) {
+                    uint8_t* err8_z, int64_t* hist8_z, int want_sam, int want_sid, double* spectral_acc,
+                    void* workspace, cudaStream_t s) {
   if (!p.ref || !p.tst) return fail(DM_EARG, "dm_spectral: null pointer");
   if (p.bands <= 0 || p.rows < 0 || p.width < 0) return fail(DM_EARG, "dm_spectral: bad geometry");
   if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_spectral: bad layout");
   if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_spectral: bad global LUT");
   if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_spectral: bad zoom LUT");
-  if ((want_sam || want_sid) && !spectral_out) return fail(DM_EARG, "dm_spectral: spectral_out is null");
+  if ((want_sam || want_sid) && (!spectral_acc || !workspace))
+    return fail(DM_EARG, "dm_spectral: spectral_acc / workspace is null");
   SpecArgs g;
   g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.bands = p.bands; g.npix = p.rows * p.width;
   const bool bip = p.layout == DM_BIP;
@@ -238,7 +239,8 @@ int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_o
   g.errmax = errmax_out;
   g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
-  g.want_sam = want_sam; g.want_sid = want_sid; g.out = spectral_out;
+  g.want_sam = want_sam; g.want_sid = want_sid;
+  g.acc = (want_sam || want_sid) ? spectral_acc : nullptr; g.ws = workspace;
   switch (p.dtype) {
     case DM_U8: return run_spectral<uint8_t>(g, bip, s);
     case DM_U16: return run_spectral<uint16_t>(g, bip, s);

@@ -323,6 +323,21 @@ def _lut_on_device(cap: float, device) -> torch.Tensor:
     return t
 
 
+_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(device) -> torch.Tensor:
+    """The zeroed device scratch dm_spectral / dm_fused_bip need (dm_workspace_bytes()), one per
+    (device, stream): launches on one stream share it, the kernels reset it themselves."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream().cuda_stream)
+    w = _WORKSPACES.get(key)
+    if w is None:
+        w = torch.zeros(int(lib().dm_workspace_bytes()) // 8 + 1, dtype=torch.int64, device=device)
+        _WORKSPACES[key] = w
+    return w
+
+
 def needs_plane(pair: DevicePair, valid) -> bool:
     return valid is not None or pair.ref_nodata is not None or pair.tst_nodata is not None
 
@@ -353,12 +368,9 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     cap_g, cap_z = want.err8_caps
     want_planes = want.errmax or cap_g is not None or cap_z is not None
     use = plane if (plane is not None and metrics_mask) else None
-    spec_blocks = None
     lut_g = lut_z = None
+    ws = workspace(dev) if (want.sam or want.sid) else None
     if want_planes or want.sam or want.sid:
-        nb = L.dm_spectral_nblocks()
-        if want.sam or want.sid:
-            spec_blocks = torch.empty(3 * nb, dtype=torch.float64, device=dev)
         if want.errmax:
             P.planes["errmax"] = torch.empty(pair.npix, dtype=torch.int16, device=dev)
         if cap_g is not None:
@@ -376,7 +388,7 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     if (want.stats and want.moments and not want.hist_bins and not want.generic_stats and not want.sid
             and (want_planes or want.sam) and pair.layout == "bip" and use is plane and want.fused):
         rc = L.dm_fused_bip(C.byref(cp), _ptr(plane), _ptr(P.sums), _ptr(P.imax), *spectral_args,
-                            1 if want.sam else 0, _ptr(spec_blocks), st)
+                            1 if want.sam else 0, _ptr(P.spec), _ptr(ws), st)
         if rc == _lib.DM_OK:
             done_stats = done_spectral = True
             P.used_mask = use is not None
@@ -389,9 +401,7 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
         P.used_mask = use is not None
     if (want_planes or want.sam or want.sid) and not done_spectral:
         check(L.dm_spectral(C.byref(cp), _ptr(plane), *spectral_args,
-                            1 if want.sam else 0, 1 if want.sid else 0, _ptr(spec_blocks), st))
-    if spec_blocks is not None:
-        P.spec.add_(spec_blocks.view(-1, 3).sum(dim=0))
+                            1 if want.sam else 0, 1 if want.sid else 0, _ptr(P.spec), _ptr(ws), st))
     if want.lmse or want.ssim_gauss:
         bsq = pair.as_bsq()
         cb = bsq.c_pair()

@@ -154,7 +154,7 @@ def error_max8_arrays(A, B, err_max_global=255, err_max_zoom=None, pct=(2, 98), 
     check(lib().dm_spectral(C.byref(cp), engine._ptr(plane), None,
                             engine._ptr(lg), lg.numel() - 1, engine._ptr(og), engine._ptr(P.hist8_g),
                             engine._ptr(lz), 0 if lz is None else lz.numel() - 1, engine._ptr(oz), engine._ptr(P.hist8_z),
-                            0, 0, None, st))
+                            0, 0, None, None, st))
     h = P.to_host()
     err8_g = og.cpu().numpy().reshape(H, W)
     err8_z = None if oz is None else oz.cpu().numpy().reshape(H, W)

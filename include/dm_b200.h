@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 2
+#define DM_ABI_VERSION 3
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -93,6 +93,11 @@ int dm_device_sm_count(void);
 /* kernels this library has launched in this process so far (bench.py reports the difference over
  * its timed region as "gpu_launches") */
 int64_t dm_launch_count(void);
+/* size in bytes of the device scratch ("workspace") that dm_spectral / dm_fused_bip take: per-block
+ * float64 partials plus the arrival counter of their in-kernel ordered final reduction.  The caller
+ * allocates it, zeroes it ONCE, and may reuse it for any number of launches on one stream (the last
+ * block of every launch resets the counter); launches on different streams need different workspaces. */
+int64_t dm_workspace_bytes(void);
 
 /* masks -------------------------------------------------------------------------------------
  * Per-pixel validity plane (uint8, rows*width), bit set = pixel selected:
@@ -125,28 +130,29 @@ int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, 
  *               device) are built by the host with the reference's own float32 expression
  *   hist8_g/hist8_z  256-bin int64 histograms of the uint8 planes (accumulated; give the
  *               STATISTICS_MEAN / STATISTICS_STDDEV tags of quicklooks.py:175-184 exactly)
- *   spectral_out  double[3*dm_spectral_nblocks()] per-block partials {sum arccos, sum sid, n}
- *               over pixels with the SPECTRAL bit (all pixels when plane == NULL), block-ordered
- *               so the host can reduce them deterministically.  Written, not accumulated.
+ *   spectral_acc  double[3] {sum arccos, sum sid, n} over pixels with the SPECTRAL bit (all pixels
+ *               when plane == NULL), ACCUMULATED: per-block partials are added up in a fixed order
+ *               by the last block of the launch (deterministic), through `workspace`
+ *               (dm_workspace_bytes(), see above)
  * want_sid = 0 skips SID (its partial is 0). */
-int dm_spectral_nblocks(void);
 int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
                 uint16_t* errmax_out,
                 const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
                 const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
-                int32_t want_sam, int32_t want_sid, double* spectral_out, void* stream);
+                int32_t want_sam, int32_t want_sid, double* spectral_acc, void* workspace, void* stream);
 
 /* one-pass BIP kernel: dm_fused_stats (moments, no histogram) + dm_spectral (error planes, SAM) from a
  * SINGLE read of both cubes -- the tile is staged once in shared memory by TMA bulk copies and
  * consumed by a per-band and a per-pixel warp group.  Same outputs and conventions as the two
- * entry points above (spectral_out: double[3*dm_spectral_nblocks()], SID slot 0).  Supports DM_BIP,
+ * entry points above (spectral_acc: double[3] accumulated, SID slot untouched).  Supports DM_BIP,
  * 16-bit samples, bands a multiple of 4 in 4..256, 16-byte aligned cubes; anything else returns
- * DM_EUNSUPPORTED and the caller uses the two separate passes. */
+ * DM_EUNSUPPORTED and the caller uses the two separate passes.  180-band cubes (EnMAP) take a kernel
+ * specialised at compile time for that pixel pitch; a partial last tile goes through the generic one. */
 int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
                  uint16_t* errmax_out,
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
                  const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
-                 int32_t want_sam, double* spectral_out, void* stream);
+                 int32_t want_sam, double* spectral_acc, void* workspace, void* stream);
 
 /* Sobel LMSE -----------------------------------------------------------------------------------
  * Replaces sobel_mag + mse in the LMSE loop (run_codec.py:123-137, 341-346): for every band,

@@ -265,7 +265,7 @@ def test_fused_bip_equals_two_pass_on_goldens(name):
     sums = torch.zeros(pair.bands * 8, dtype=torch.int64, device="cuda")
     maxs = torch.zeros_like(sums)
     rc = _lib.lib().dm_fused_bip(C.byref(pair.c_pair()), None, sums.data_ptr(), maxs.data_ptr(), None, None, 0, None,
-                                 None, None, 0, None, None, 0, None, None)
+                                 None, None, 0, None, None, 0, None, None, None)
     assert rc == _lib.DM_OK, _lib.lib().dm_last_error()
     assert int(sums[0].item()) == pair.npix
 
