@@ -82,7 +82,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.001)
 
     def start(self):
         if self._nv is not None:
@@ -200,7 +200,7 @@ def make_device_pairs(torch, n_pairs: int, seed: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,16 +230,15 @@ def main():
     # ---- device-resident arm -------------------------------------------------------------------
     n_pairs = 3                                   # 2.26 GB rotating, every pair 6x the 126 MB L2
     pairs = make_device_pairs(torch, n_pairs, seed=rank + 1)
-    outs = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(n_pairs)]
+    # every step writes its own zeroed partial vector (31.5 KB), like the pairs of a rate sweep: no
+    # memset inside the timed region, and with N GPUs no wait for the previous combine of a buffer
+    outs = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(args.warmup + args.steps)]
 
     from image_compression_analysis_b200.sharding import PipelinedCombiner
     combiner = PipelinedCombiner() if world > 1 else None
 
     def step(i):
-        P = outs[i % n_pairs]
-        if combiner is not None:
-            combiner.before_reuse(P)
-        P.zero_()
+        P = outs[i]
         evaluate(pairs[i % n_pairs], want, out=P)
         if combiner is not None:
             combiner.combine(P)               # side stream: overlaps the next pair's kernel
@@ -271,15 +270,19 @@ def main():
     launches = L.dm_launch_count() - launches0
     clocks = sampler.stop()
 
-    # per-launch timing of the step's kernel: the same launches with events around each one
+    # per-launch timing of the step's kernel: the same launches with CUDA events around each one on the
+    # launching stream.  A short spin kernel is queued first so that both events and the launch are
+    # already in the stream when the GPU reaches them (the event delta is then the kernel, not the
+    # host's launch path).
     kern_ms = {"dm_fused_bip": []}
     if combiner is not None:
         combiner.wait_all()
-    for i in range(args.steps):
-        P = outs[i % n_pairs]
-        P.zero_()
+    scratch = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(min(args.steps, 50))]
+    torch.cuda.synchronize()
+    for i, P in enumerate(scratch):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = L.dm_launch_count()
+        torch.cuda._sleep(400_000)
         a.record()
         evaluate(pairs[i % n_pairs], want, out=P)
         b.record()
@@ -295,7 +298,7 @@ def main():
     value = world * PAIR_BYTES * args.steps / (ms_total * 1e-3) / 1e9
 
     # sanity: the step's result must be a real metric dict (guards against timing a no-op)
-    Pchk = step(0)
+    Pchk = outs[-1]
     if combiner is not None:
         combiner.wait_all()
     h = Pchk.to_host()
@@ -374,13 +377,15 @@ def main():
                    "sharding": ("row strips, one per GPU; every step ends with the combine of the integer/float64 partials "
                                 "(one NCCL all-gather + dm_combine_partials) on a side stream, overlapped with the next "
                                 "pair's kernel; the timed region ends after the last combine") if world > 1 else "single GPU",
-                   "kernels_per_step": ["dm_fused_bip (fused_bip_kernel: per-band stats + per-pixel SAM, one read)"]},
+                   "kernels_per_step": ["dm_fused_bip (fused_ct_kernel<180>: per-band stats + per-pixel SAM from one read, "
+                                        "SAM partials reduced in-kernel)"]},
         "frac_of_hbm_peak": value / (world * peak),
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": UNIT,
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": PAIR_BYTES,
                      "launch_ms": {dominant: dom_ms},
-                     "note": "launch_ms includes the small torch reductions of the per-block SAM partials that follow the kernel"},
+                     "note": "launch_ms: CUDA events around each single launch on the launching stream, queued behind a "
+                             "spin kernel so that the host launch path is not inside the interval"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -28,6 +28,10 @@
 
 #include "dm_common.cuh"
 
+#ifndef DM_POLL_NS
+#define DM_POLL_NS 64
+#endif
+
 namespace dm {
 
 namespace {
@@ -66,6 +70,7 @@ struct FusedArgs {
   int want_sam;
   int debug;                  // experiments only (DM_FUSED_DEBUG): 1 = producer skips the copies,
                               // 2 = band group skips its arithmetic, 4 = pixel group skips its arithmetic
+  uint32_t zero;              // 0 (an operand the compiler cannot fold, see band_word)
   double* spec_acc;           // {sum arccos, -, n}, accumulated (ordered_block_sum3)
   void* ws;
 };
@@ -112,11 +117,12 @@ __device__ __forceinline__ int hmax2s(uint32_t p) { return max((int)(short)(p & 
 // per-band packed accumulators (same scheme as stats.cu)
 struct BandAccS {
   uint32_t sabs, sx, sy, xxl, xxh, yyl, yyh, xyl, xyh, maxd;
+  uint32_t zero;      // always 0, but loaded from the kernel arguments (see band_word)
 };
 struct BandAcc : BandAccS {
   unsigned long long t_abs, t_x, t_y, t_xx, t_yy, t_xy;
   __device__ __forceinline__ void reset() {
-    sabs = sx = sy = xxl = xxh = yyl = yyh = xyl = xyh = maxd = 0;
+    sabs = sx = sy = xxl = xxh = yyl = yyh = xyl = xyh = maxd = 0; zero = 0;
     t_abs = t_x = t_y = t_xx = t_yy = t_xy = 0;
   }
   __device__ __forceinline__ void spill() {
@@ -132,7 +138,9 @@ struct BandAcc : BandAccS {
 // takes the maxima of the natural words instead, two words per VIMNMX3)
 template <bool PAIR, bool TRACK>
 __device__ __forceinline__ void band_word(BandAccS& a, uint32_t x, uint32_t y, uint32_t& maxsel_u) {
-  const uint32_t mx = vmaxu2(x, y), mn = vminu2(x, y), d = mx - mn;
+  // three-input add with an operand the compiler cannot fold: IADD3 on the ALU pipe instead of an
+  // IMAD.IADD on the FMA pipe, which the dp2a stream already saturates
+  const uint32_t mx = vmaxu2(x, y), mn = vminu2(x, y), d = mx - mn + a.zero;
   if (TRACK) maxsel_u = vmaxu2(maxsel_u, mx);
   a.maxd = vmaxu2(a.maxd, d);
   const uint32_t ones = PAIR ? 0x0101u : 0x0001u;
@@ -533,16 +541,22 @@ template <int BANDS> struct Geo {
 };
 
 // barrier helpers on raw shared-memory addresses (computed once per thread, not per tile)
+constexpr unsigned kPollNs = DM_POLL_NS;
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  // One try_wait (the hardware suspends the warp for a while when the phase is not complete), then
+  // poll at a coarse interval: the bulk copy signals the barrier once per 2 KB granule, and a waiter
+  // that wakes on every one of those spends issue slots that the working warps need.
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
+      "WAIT_%=:\n"
+      "nanosleep.u32 %2;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(kPollNs) : "memory");
 }
 // arrive and tell whether this was the LAST pending arrival of the phase (exactly one arriver sees it)
 __device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
@@ -635,7 +649,7 @@ fused_ct_kernel(FusedArgs g) {
     const uint32_t ld_off = ring + (uint32_t)(lane & 7) * (2u * G::PIXB) + (uint32_t)mchunk * 16u;
     BandAccS a[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; }
+    for (int j = 0; j < 4; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; a[j].zero = g.zero; }
     uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
     uint32_t n0 = 0, n1 = 0;                           // MASK: selected even / odd pixels of this thread's rows
 
@@ -984,7 +998,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (want_sam && (!spectral_acc || !workspace)) return fail(DM_EARG, "dm_fused_bip: spectral_acc / workspace is null");
   FusedArgs g;
   g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
-  g.P = 0; g.ntiles = 0; g.tail_pixels = 0;
+  g.P = 0; g.ntiles = 0; g.tail_pixels = 0; g.zero = 0;
   g.sums = sums; g.maxs = maxs; g.errmax = errmax_out;
   g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
