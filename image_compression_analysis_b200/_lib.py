@@ -54,6 +54,7 @@ SYMBOLS = {
                               C.c_int32, C.c_int32, _P, _P, _P]),
     "dm_fused_bip": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                C.c_int32, _P, _P, _P]),
+    "dm_fused_bsq": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "dm_sobel_nblocks": (C.c_int, []),
     "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_ssim_nblocks": (C.c_int, []),

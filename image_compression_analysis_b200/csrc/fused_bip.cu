@@ -71,6 +71,7 @@ struct FusedArgs {
   int debug;                  // experiments only (DM_FUSED_DEBUG): 1 = producer skips the copies,
                               // 2 = band group skips its arithmetic, 4 = pixel group skips its arithmetic
   uint32_t zero;              // 0 (an operand the compiler cannot fold, see band_word)
+  uint32_t poll_ns;           // barrier polling interval (DM_POLL_NS, default kPollNs)
   double* spec_acc;           // {sum arccos, -, n}, accumulated (ordered_block_sum3)
   void* ws;
 };
@@ -542,7 +543,7 @@ template <int BANDS> struct Geo {
 
 // barrier helpers on raw shared-memory addresses (computed once per thread, not per tile)
 constexpr unsigned kPollNs = DM_POLL_NS;
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, uint32_t poll_ns) {
   // One try_wait (the hardware suspends the warp for a while when the phase is not complete), then
   // poll at a coarse interval: the bulk copy signals the barrier once per 2 KB granule, and a waiter
   // that wakes on every one of those spends issue slots that the working warps need.
@@ -556,7 +557,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@!p bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(kPollNs) : "memory");
+      "}\n" ::"r"(bar), "r"(parity), "r"(poll_ns) : "memory");
 }
 // arrive and tell whether this was the LAST pending arrival of the phase (exactly one arriver sees it)
 __device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
@@ -597,7 +598,9 @@ fused_ct_kernel(FusedArgs g) {
   // tiles of this CTA: local index it = 0 .. my_tiles-1 is global tile blockIdx.x + it*gridDim.x and
   // lives in stage it % kStages (full tiles only; the launcher hands a partial tile to the generic kernel)
   const int my_tiles = (int64_t)blockIdx.x < g.ntiles ? (int)((g.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-  const int dbg = g.debug;
+  // no per-pixel output requested (stats only): the pixel warps just hand their stages back
+  const int dbg = g.debug | ((ERR || g.want_sam) ? 0 : 4);
+  const uint32_t poll_ns = g.poll_ns;
   const uint32_t ring = smem_u32(smem);
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
 
@@ -620,7 +623,7 @@ fused_ct_kernel(FusedArgs g) {
   auto release_tile = [&](int it) {
     const uint32_t eb = empty0 + 8u * (uint32_t)(it & (kStages - 1));
     if (mbar_arrive_is_last_a(eb)) {
-      mbar_wait_a(eb, (uint32_t)((it / kStages) & 1));
+      mbar_wait_a(eb, (uint32_t)((it / kStages) & 1), poll_ns);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       issue_tile(it + kStages);
     }
@@ -680,7 +683,7 @@ fused_ct_kernel(FusedArgs g) {
         const int it1 = it0 + EPOCH < my_tiles ? it0 + EPOCH : my_tiles;
         for (int it = it0; it < it1; ++it) {
           const int s = it & (kStages - 1);
-          mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1));
+          mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
           if (!(dbg & 2)) {
             const uint32_t xs = ld_off + (uint32_t)s * G::STAGE;
             const uint8_t* pl = MASK ? g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P : nullptr;
@@ -843,7 +846,7 @@ fused_ct_kernel(FusedArgs g) {
     int visit = 0;
     for (int it = grp; it < my_tiles; it += 2, ++visit) {
       const int s = it & (kStages - 1);
-      mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1));
+      mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
       uint32_t emax = 0;
       uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0, sx = 0, sy = 0;
       if (!(dbg & 4)) {
@@ -1004,6 +1007,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
   g.want_sam = want_sam; g.spec_acc = want_sam ? spectral_acc : nullptr; g.ws = workspace;
   { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
   if (g.npix <= 0) return DM_OK;
   const bool force_generic = (g.debug & 8) != 0;
   if (B == 180 && g.npix >= kTilePixels && !force_generic) {

@@ -83,6 +83,14 @@ int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
                           hist8_z, want_sam, spectral_acc, workspace, static_cast<cudaStream_t>(stream));
 }
 
+int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
+                 const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z,
+                 int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_fused_bsq: null pair");
+  return launch_fused_bsq(*p, plane, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
+                          hist8_z, static_cast<cudaStream_t>(stream));
+}
+
 int dm_sobel_nblocks(void) { return sobel_nblocks(); }
 
 int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,

@@ -154,6 +154,16 @@ int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
                  const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
                  int32_t want_sam, double* spectral_acc, void* workspace, void* stream);
 
+/* one-pass BSQ kernel for few-band cubes (Sentinel-2 Case A): dm_fused_stats (moments, no histogram)
+ * + the error planes of dm_spectral from a SINGLE read -- a thread loads the same 8-pixel vector of
+ * every band, so it holds whole spectra.  Same outputs and conventions as those two entry points.
+ * Supports DM_BSQ, 16-bit samples, 1..4 bands, bands starting on 16-byte boundaries, caps <= 255;
+ * anything else returns DM_EUNSUPPORTED and the caller uses the two separate passes. */
+int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
+                 uint16_t* errmax_out,
+                 const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                 const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, void* stream);
+
 /* Sobel LMSE -----------------------------------------------------------------------------------
  * Replaces sobel_mag + mse in the LMSE loop (run_codec.py:123-137, 341-346): for every band,
  * sum over pixels of (|grad ref| - |grad tst|)^2 with the 3x3 Sobel pair and edge replication.

@@ -302,6 +302,85 @@ def test_fused_bip_vs_oracle(dtype, B, H, W, amp, masked):
     assert _close(sam_got, sam_want), (sam_got, sam_want)
 
 
+def _fused_bsq_vs_separate(ref, dec, valid, ref_nodata=None, tst_nodata=None, caps=(255, 32)):
+    """dm_fused_bsq (one pass) against dm_fused_stats + dm_spectral (two passes), BSQ cubes of <= 4 bands."""
+    import ctypes as C
+    import torch
+    from image_compression_analysis_b200 import _lib
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    from image_compression_analysis_b200.metrics import _valid_to_device
+    B, H, W = ref.shape
+    pair = DevicePair.from_arrays(ref, dec, "bsq", ref_nodata, tst_nodata)
+    vdev = _valid_to_device(valid, H, W, "shape")
+    outs = []
+    l0 = _lib.lib().dm_launch_count()
+    for fused in (True, False):
+        P = evaluate(pair, Want(stats=True, errmax=True, err8_caps=caps, fused=fused), vdev)
+        torch.cuda.synchronize()
+        outs.append((P.to_host(), {k: v.cpu().numpy() for k, v in P.planes.items()}))
+    (hf, pf), (hs, ps) = outs
+    assert np.array_equal(hf.isum, hs.isum)
+    assert np.array_equal(hf.imax.reshape(-1, 8).max(0)[1:], hs.imax.reshape(-1, 8).max(0)[1:])   # cube-wide maxima
+    assert np.array_equal(hf.maxs[:, 0], hs.maxs[:, 0])                                           # per-band max|d|
+    for k in ("errmax", "err8_g", "err8_z"):
+        if k in ps:
+            assert np.array_equal(pf[k], ps[k]), k
+    # and the one-pass kernel really ran: a direct call must not answer DM_EUNSUPPORTED
+    sums = torch.zeros(B * 8, dtype=torch.int64, device="cuda")
+    maxs = torch.zeros_like(sums)
+    rc = _lib.lib().dm_fused_bsq(C.byref(pair.c_pair()), None, sums.data_ptr(), maxs.data_ptr(), None, None, 0, None,
+                                 None, None, 0, None, None, None)
+    if B == 1 or (H * W) % 8 == 0:            # bands of a packed (B,H,W) array start on 16-byte boundaries
+        assert rc == _lib.DM_OK, _lib.lib().dm_last_error()
+        assert int(sums[0].item()) == H * W
+    else:
+        assert rc == _lib.DM_EUNSUPPORTED
+    return hf, pf
+
+
+@pytest.mark.parametrize("name", ["a_gauss", "a_identical", "a_near3_masked", "a_mask_all_false", "single_band_odd"])
+def test_fused_bsq_equals_two_pass_on_goldens(name):
+    c = goldenio.load(name)
+    if c["ref"].shape[0] > 4 or c["ref"].dtype == np.uint8:
+        pytest.skip("dm_fused_bsq handles 16-bit cubes of up to 4 bands")
+    _fused_bsq_vs_separate(c["ref"], c["tst"], c["valid"], c["ref_nodata"], c["tst_nodata"])
+
+
+@pytest.mark.parametrize("dtype,B,H,W,amp,masked,caps", [
+    ("uint16", 4, 256, 512, 40, False, (255, 32)),
+    ("uint16", 4, 257, 515, 300, True, (255, 32)),      # odd pixel count: scalar tail; errors above both caps
+    ("uint16", 4, 128, 256, 65535, False, (255, None)),  # full-range errors, every partial at its bound
+    ("int16", 3, 130, 264, 3000, True, (100, 7)),
+    ("int16", 1, 64, 1000, 65535, False, (255, 32)),
+    ("uint16", 2, 3, 2, 9, False, (255, 32)),            # fewer than eight pixels
+])
+def test_fused_bsq_vs_oracle(dtype, B, H, W, amp, masked, caps):
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200.engine import dtype_code
+    from oracle import distortion_oracle as orc
+    ref, dec = _rand_pair(21, dtype, B, H, W, amp)
+    if amp == 65535 and dtype == "uint16":
+        ref[:, :8] = 65535; dec[:, :8] = 0
+    valid = (np.random.default_rng(22).random((H, W)) < 0.6) if masked else None
+    hf, pf = _fused_bsq_vs_separate(ref, dec, valid, caps=caps)
+    got = finish.finish_compute_metrics(dtype_code(dtype), hf.sums, hf.maxs)
+    want = orc.compute_metrics(ref, dec, valid, extras=False)
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, int):
+            assert g == w, (k, g, w)
+        elif k.startswith("psnr"):
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+        else:
+            assert _close(g, w, rel=1e-9), (k, g, w)
+    o = orc.error_max8(ref, dec, caps[0], caps[1])
+    assert np.array_equal(pf["err8_g"].reshape(H, W), o["err8_g"])
+    if caps[1] is not None:
+        assert np.array_equal(pf["err8_z"].reshape(H, W), o["err8_z"])
+        assert np.array_equal(np.bincount(o["err8_z"].ravel(), minlength=256), hf.hist8_z)
+    assert np.array_equal(np.bincount(o["err8_g"].ravel(), minlength=256), hf.hist8_g)
+
+
 def test_combine_partials_kernel():
     """dm_combine_partials (the reduction after the multi-GPU all-gather) against numpy."""
     import ctypes as C

@@ -55,6 +55,8 @@ def main():
             "stats+sam (fused if bip)": Want(stats=True, sam=True),
             "stats+sam+err8 (fused if bip)": Want(stats=True, sam=True, err8_caps=(255, 32)),
             "spectral errmax+err8": Want(stats=False, err8_caps=(255, 32)),
+            "stats+err8 (fused if <=4 bands bsq)": Want(stats=True, err8_caps=(255, 32)),
+            "stats+err8 two passes": Want(stats=True, err8_caps=(255, 32), fused=False),
         }
         if args.what == "all":
             variants["spectral sam+sid"] = Want(stats=False, sam=True, sid=True)
