@@ -34,6 +34,7 @@ METRIC = "distortion-metric throughput (original+decoded image-pair bytes)"
 UNIT = "GB/s"
 BANDS, ROWS, WIDTH = 180, 1024, 1024
 PAIR_BYTES = 2 * 2 * BANDS * ROWS * WIDTH            # 754 974 720: SURVEY.md 8d algorithmic bytes
+COMBINE_BATCH = 8                                    # pairs per multi-GPU exchange (latency bound, a few KB per pair)
 WORKLOAD = "Case B EnMAP 1024x1024x180 uint16 BIP cube pair per GPU: compute_metrics (per-band+global PSNR/SSIM/MAXAE) + SAM"
 
 
@@ -232,16 +233,18 @@ def main():
     pairs = make_device_pairs(torch, n_pairs, seed=rank + 1)
     # every step writes its own zeroed partial vector (31.5 KB), like the pairs of a rate sweep: no
     # memset inside the timed region, and with N GPUs no wait for the previous combine of a buffer
-    outs = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(args.warmup + args.steps)]
+    # (the vectors of the run are contiguous, so with N GPUs a batch of them is exchanged with ONE
+    # all-gather + dm_combine_partials on a side stream: the exchange is latency bound)
+    run, outs = Partials.allocate_run(args.warmup + args.steps, BANDS, 0, pairs[0].ref.device, "uint16")
 
-    from image_compression_analysis_b200.sharding import PipelinedCombiner
-    combiner = PipelinedCombiner() if world > 1 else None
+    from image_compression_analysis_b200.sharding import RunCombiner
+    combiner = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH) if world > 1 else None
 
     def step(i):
         P = outs[i]
         evaluate(pairs[i % n_pairs], want, out=P)
         if combiner is not None:
-            combiner.combine(P)               # side stream: overlaps the next pair's kernel
+            combiner.done(i)                  # every COMBINE_BATCH pairs: one exchange, overlapped
         return P
 
     def barrier():
@@ -252,7 +255,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     if combiner is not None:
-        combiner.wait_all()
+        combiner.finish(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -263,7 +266,7 @@ def main():
     for i in range(args.steps):
         step(args.warmup + i)
     if combiner is not None:
-        combiner.wait_all()                   # the timed region ends when the last combine has finished
+        combiner.finish(args.warmup + args.steps)   # the timed region ends when the last combine has finished
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -275,8 +278,6 @@ def main():
     # already in the stream when the GPU reaches them (the event delta is then the kernel, not the
     # host's launch path).
     kern_ms = {"dm_fused_bip": []}
-    if combiner is not None:
-        combiner.wait_all()
     scratch = [Partials.allocate(BANDS, 0, pairs[0].ref.device, "uint16") for _ in range(min(args.steps, 50))]
     torch.cuda.synchronize()
     for i, P in enumerate(scratch):
@@ -299,8 +300,6 @@ def main():
 
     # sanity: the step's result must be a real metric dict (guards against timing a no-op)
     Pchk = outs[-1]
-    if combiner is not None:
-        combiner.wait_all()
     h = Pchk.to_host()
     torch.cuda.synchronize()
     res = finish.finish_compute_metrics(_lib.DM_U16, h.sums, h.maxs)
@@ -374,9 +373,9 @@ def main():
         "dtype": "u16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "layout": "bip", "bands": BANDS, "rows_per_gpu": ROWS, "width": WIDTH,
                    "pair_bytes_per_gpu": PAIR_BYTES, "l2_policy": f"inputs larger than L2: {n_pairs} distinct 755 MB pairs rotated",
-                   "sharding": ("row strips, one per GPU; every step ends with the combine of the integer/float64 partials "
-                                "(one NCCL all-gather + dm_combine_partials) on a side stream, overlapped with the next "
-                                "pair's kernel; the timed region ends after the last combine") if world > 1 else "single GPU",
+                   "sharding": (f"row strips, one per GPU; the integer/float64 partials of every {COMBINE_BATCH} pairs are combined "
+                                "with one NCCL all-gather + dm_combine_partials on a side stream, overlapped with the next "
+                                "pairs' kernels; the timed region ends after the last combine") if world > 1 else "single GPU",
                    "kernels_per_step": ["dm_fused_bip (fused_ct_kernel<180>: per-band stats + per-pixel SAM from one read, "
                                         "SAM partials reduced in-kernel)"]},
         "frac_of_hbm_peak": value / (world * peak),

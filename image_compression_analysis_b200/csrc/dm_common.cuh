@@ -60,8 +60,8 @@ int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t
                  int64_t img_rows, double* out, cudaStream_t s);
 int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t row_end,
                       int64_t img_row0, int64_t img_rows, double* out, cudaStream_t s);
-int launch_combine_partials(const void* gathered, int world, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out,
-                            cudaStream_t s);
+int launch_combine_partials(const void* gathered, int world, int64_t records, int64_t n_sum, int64_t n_max,
+                            int64_t n_f64, void* out, cudaStream_t s);
 int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands, int64_t rows,
                       int64_t width, cudaStream_t s);
 

@@ -108,9 +108,9 @@ int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int6
                            static_cast<cudaStream_t>(stream));
 }
 
-int dm_combine_partials(const void* gathered, int32_t world, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out,
-                        void* stream) {
-  return launch_combine_partials(gathered, world, n_sum, n_max, n_f64, out, static_cast<cudaStream_t>(stream));
+int dm_combine_partials(const void* gathered, int32_t world, int64_t records, int64_t n_sum, int64_t n_max, int64_t n_f64,
+                        void* out, void* stream) {
+  return launch_combine_partials(gathered, world, records, n_sum, n_max, n_f64, out, static_cast<cudaStream_t>(stream));
 }
 
 int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands, int64_t rows,

@@ -200,6 +200,43 @@ class Partials:
         P.flat = flat
         return P
 
+    @staticmethod
+    def allocate_run(n: int, bands: int, hist_bins: int, device, np_dtype: str):
+        """`n` zeroed partial vectors in ONE contiguous buffer (the pairs of a sweep): returns
+        (run, [Partials...]) where every Partials is a view of run[i].  A contiguous range of the run
+        combines across GPUs with one all-gather (`allreduce_run_`)."""
+        ni, nm, nf = Partials.sizes(bands, hist_bins)
+        L = ni + nm + nf
+        run = torch.zeros((n, L), dtype=torch.int64, device=device)
+        out = []
+        for i in range(n):
+            flat = run[i]
+            P = Partials(bands, hist_bins, flat[:ni], flat[ni:ni + nm], flat[ni + nm:].view(torch.float64), {}, np_dtype)
+            P.flat = flat
+            out.append(P)
+        return run, out
+
+    @staticmethod
+    def allreduce_run_(run: torch.Tensor, i0: int, i1: int, bands: int, hist_bins: int, group=None) -> None:
+        """Combine the partial vectors run[i0:i1] of all ranks in place with ONE all-gather +
+        dm_combine_partials: the exchange is latency bound, so a sweep batches several pairs per call."""
+        import torch.distributed as dist
+        if i1 <= i0 or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        world = dist.get_world_size(group)
+        ni, nm, nf = Partials.sizes(bands, hist_bins)
+        part = run[i0:i1]
+        if not run.is_cuda:                     # gloo (the CPU tests): three all-reduces on the column blocks
+            a, b, c = part[:, :ni].contiguous(), part[:, ni:ni + nm].contiguous(), part[:, ni + nm:].contiguous().view(torch.float64)
+            dist.all_reduce(a, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+            part[:, :ni], part[:, ni:ni + nm], part[:, ni + nm:] = a, b, c.view(torch.int64)
+            return
+        gathered = torch.empty((world,) + tuple(part.shape), dtype=torch.int64, device=run.device)
+        dist.all_gather_into_tensor(gathered, part, group=group)
+        check(lib().dm_combine_partials(_ptr(gathered), world, i1 - i0, ni, nm, nf, _ptr(part), _stream_ptr()))
+
     def zero_(self) -> "Partials":
         self.flat.zero_()
         return self
@@ -251,7 +288,7 @@ class Partials:
         if self.flat is not None and self.flat.is_cuda:
             gathered = torch.empty(world * self.flat.numel(), dtype=torch.int64, device=self.flat.device)
             dist.all_gather_into_tensor(gathered, self.flat, group=group)
-            check(lib().dm_combine_partials(_ptr(gathered), world, self.isum.numel(), self.imax.numel(),
+            check(lib().dm_combine_partials(_ptr(gathered), world, 1, self.isum.numel(), self.imax.numel(),
                                             self.fsum.numel(), _ptr(self.flat), _stream_ptr()))
             return self
         works = [dist.all_reduce(self.isum, op=dist.ReduceOp.SUM, group=group, async_op=True),

@@ -139,3 +139,40 @@ class PipelinedCombiner:
         import torch
         torch.cuda.current_stream().wait_stream(self.stream)
         self._done.clear()
+
+
+class RunCombiner:
+    """Combine the pairs of a sweep in batches: the partial vectors of the sweep live in one contiguous
+    run (`Partials.allocate_run`), and every `batch` finished pairs are exchanged with ONE all-gather
+    + dm_combine_partials on a side stream, behind an event, while the next pairs' kernels run.  The
+    exchange is a few KB per pair and latency bound, so batching divides its cost (and the host's
+    launch work) by `batch` without delaying anything a sweep needs before its end."""
+
+    def __init__(self, run, bands: int, hist_bins: int = 0, batch: int = 8, group=None):
+        import torch
+        self.run, self.bands, self.hist_bins, self.batch, self.group = run, bands, hist_bins, max(1, batch), group
+        self.stream = torch.cuda.Stream()
+        self._next = 0          # first record not yet combined
+
+    def done(self, i: int) -> None:
+        """Record i (and everything before it) has been queued on the current stream."""
+        if i + 1 - self._next >= self.batch:
+            self._flush(i + 1)
+
+    def _flush(self, upto: int) -> None:
+        import torch
+        from .engine import Partials
+        if upto <= self._next:
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            Partials.allreduce_run_(self.run, self._next, upto, self.bands, self.hist_bins, self.group)
+        self._next = upto
+
+    def finish(self, upto: int) -> None:
+        """Combine what is left up to record `upto` and make the current stream wait for it."""
+        import torch
+        self._flush(upto)
+        torch.cuda.current_stream().wait_stream(self.stream)

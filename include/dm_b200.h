@@ -185,12 +185,14 @@ int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int6
                   int64_t img_row0, int64_t img_rows, double* out, void* stream);
 
 /* multi-GPU combine ----------------------------------------------------------------------------
- * After ONE all-gather of every rank's flat partial vector [n_sum int64 | n_max int64 | n_f64 double]
- * (the layout of engine.Partials) this reduces the `world` gathered vectors into `out` (same
- * layout): int64 sums added, int64 maxima maxed, float64 sums added in RANK ORDER, so the result is
- * bit-identical on every rank and from run to run.  gathered: world x (n_sum+n_max+n_f64) 8-byte words. */
-int dm_combine_partials(const void* gathered, int32_t world, int64_t n_sum, int64_t n_max, int64_t n_f64,
-                        void* out, void* stream);
+ * After ONE all-gather of every rank's run of `records` flat partial vectors, each
+ * [n_sum int64 | n_max int64 | n_f64 double] (the layout of engine.Partials; a run is the partials of
+ * `records` consecutive pairs of a sweep), this reduces the `world` gathered runs into `out` (one run,
+ * same layout): int64 sums added, int64 maxima maxed, float64 sums added in RANK ORDER, so the result
+ * is bit-identical on every rank and from run to run.
+ * gathered: world x records x (n_sum+n_max+n_f64) 8-byte words. */
+int dm_combine_partials(const void* gathered, int32_t world, int64_t records, int64_t n_sum, int64_t n_max,
+                        int64_t n_f64, void* out, void* stream);
 
 /* layout helper: (rows,width,bands) -> (bands,rows,width), same dtype (1 or 2 bytes/sample) */
 int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands, int64_t rows,

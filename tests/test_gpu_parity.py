@@ -381,7 +381,8 @@ def test_fused_bsq_vs_oracle(dtype, B, H, W, amp, masked, caps):
     assert np.array_equal(np.bincount(o["err8_g"].ravel(), minlength=256), hf.hist8_g)
 
 
-def test_combine_partials_kernel():
+@pytest.mark.parametrize("records", [1, 5])
+def test_combine_partials_kernel(records):
     """dm_combine_partials (the reduction after the multi-GPU all-gather) against numpy."""
     import ctypes as C
     import torch
@@ -389,20 +390,21 @@ def test_combine_partials_kernel():
     rng = np.random.default_rng(3)
     world, ns, nm, nf = 8, 1443, 1440, 543
     L = ns + nm + nf
-    G = np.zeros((world, L), np.int64)
-    G[:, :ns + nm] = rng.integers(-2**40, 2**40, size=(world, ns + nm))
-    F = rng.standard_normal((world, nf)) * 1e6
-    G[:, ns + nm:] = F.view(np.int64)
+    G = np.zeros((world, records, L), np.int64)
+    G[:, :, :ns + nm] = rng.integers(-2**40, 2**40, size=(world, records, ns + nm))
+    F = rng.standard_normal((world, records, nf)) * 1e6
+    G[:, :, ns + nm:] = F.view(np.int64)
     g = torch.from_numpy(G).cuda()
-    out = torch.zeros(L, dtype=torch.int64, device="cuda")
-    _lib.check(_lib.lib().dm_combine_partials(C.c_void_p(g.data_ptr()), world, ns, nm, nf, C.c_void_p(out.data_ptr()), None))
-    o = out.cpu().numpy()
-    assert np.array_equal(o[:ns], G[:, :ns].sum(0))
-    assert np.array_equal(o[ns:ns + nm], G[:, ns:ns + nm].max(0))
-    want = np.zeros(nf)
+    out = torch.zeros(records * L, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().dm_combine_partials(C.c_void_p(g.data_ptr()), world, records, ns, nm, nf,
+                                              C.c_void_p(out.data_ptr()), None))
+    o = out.cpu().numpy().reshape(records, L)
+    assert np.array_equal(o[:, :ns], G[:, :, :ns].sum(0))
+    assert np.array_equal(o[:, ns:ns + nm], G[:, :, ns:ns + nm].max(0))
+    want = np.zeros((records, nf))
     for r in range(world):
         want = want + F[r]                      # rank order, like the kernel
-    assert np.array_equal(o[ns + nm:].view(np.float64), want)
+    assert np.array_equal(o[:, ns + nm:].view(np.float64), want)
 
 
 def test_launcher_rebinds_the_reference_module(tmp_path):

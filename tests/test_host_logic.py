@@ -159,6 +159,18 @@ for k, w in c["compute_metrics"].items():
     ok = (g == w) if (isinstance(w, int) or k.startswith("psnr")) else goldenio.close(g, w, rel=1e-12)
     assert ok, (k, g, w)
 assert h.spec[2] == H * W and abs(h.spec[0] - 0.25 * sum(range(1, world + 1))) < 1e-15
+# the same through a RUN of partial vectors (the pairs of a sweep, one exchange for several of them)
+run, Ps = Partials.allocate_run(3, B, 0, torch.device("cpu"), "uint16")
+for i, Q in enumerate(Ps):
+    Q.sums.copy_(torch.from_numpy(S.reshape(-1)) * (i + 1))
+    Q.imax.copy_(torch.from_numpy(M.reshape(-1)) + i)
+    Q.spec.copy_(torch.tensor([0.5 * (rank + 1) + i, 0.0, float(s.rows * W)], dtype=torch.float64))
+Partials.allreduce_run_(run, 1, 3, B, 0)
+h0, h2 = Ps[0].to_host(), Ps[2].to_host()
+assert np.array_equal(h0.sums, S)                                   # outside the exchanged range: untouched
+assert np.array_equal(h2.sums[:, 0], np.full(B, 3 * H * W))          # N of record 2: 3 x the image's pixels
+assert np.array_equal(h2.maxs[:, 0], h.maxs[:, 0] + 2)
+assert h2.spec[2] == H * W and abs(h2.spec[0] - (0.5 * sum(range(1, world + 1)) + 2 * world)) < 1e-12
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
