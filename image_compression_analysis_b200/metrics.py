@@ -134,21 +134,15 @@ def compute_metrics_arrays(ref, tst, valid=None, *, ref_nodata=None, tst_nodata=
     """compute_metrics on in-memory cubes.  Returns the reference's keys; with extras=True also the
     MAE / SSE / histogram additions (new keys only)."""
     pair = DevicePair.from_arrays(ref, tst, layout, ref_nodata, tst_nodata)
+    return compute_metrics_pair(pair, valid, hist_bins=hist_bins, extras=extras)
+
+
+def compute_metrics_pair(pair: DevicePair, valid=None, *, hist_bins: int = 0, extras: bool = False) -> Dict[str, float]:
+    """compute_metrics on a device-resident pair."""
     vdev = _valid_to_device(valid, pair.rows, pair.width, f"Mask shape {None if valid is None else valid.shape} != {(pair.rows, pair.width)}")
     P = metrics_partials(pair, vdev, Want(stats=True, hist_bins=hist_bins))
     h = P.to_host()
     return finish.finish_compute_metrics(dtype_code(pair.np_dtype), h.sums, h.maxs, h.hist, extras=extras)
-
-
-def _read_pair(ref_path, tst_path):
-    with open_raster(ref_path) as ref, open_raster(tst_path) as tst:
-        assert ref.count == tst.count and ref.width == tst.width and ref.height == tst.height, \
-            "Reference and test must match in size and band count."
-        A = ref.read()
-        R = tst.read()
-        info = dict(ref_nodata=ref.nodata, tst_nodata=tst.nodata, ref_mask=explicit_mask(ref),
-                    tst_mask=explicit_mask(tst), H=ref.height, W=ref.width, B=ref.count)
-    return A, R, info
 
 
 def _fold_masks(valid, info):
@@ -162,11 +156,11 @@ def _fold_masks(valid, info):
 
 def compute_metrics(ref_path: Path, tst_path: Path, valid: Optional[np.ndarray] = None) -> Dict[str, float]:
     """Compute PSNR/SSIM per band + global PSNR/SSIM and per-band max|d| (run_codec.py:240-304)."""
-    A, R, info = _read_pair(ref_path, tst_path)
+    from .ingest import load_pair
+    pair, info = load_pair(ref_path, tst_path)          # read once per rep, shared with the other two calls
     if valid is not None and tuple(valid.shape) != (info["H"], info["W"]):
         raise ValueError(f"Mask shape {valid.shape} != {(info['H'], info['W'])}")
-    return compute_metrics_arrays(A, R, _fold_masks(valid, info), ref_nodata=info["ref_nodata"],
-                                  tst_nodata=info["tst_nodata"])
+    return compute_metrics_pair(pair, _fold_masks(valid, info))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,6 +171,11 @@ def compute_metrics(ref_path: Path, tst_path: Path, valid: Optional[np.ndarray] 
 def compute_sam_sid_lmse_caseB_arrays(ref, tst, valid=None, *, ref_nodata=None, tst_nodata=None,
                                       layout: str = "bsq") -> Dict[str, float]:
     pair = DevicePair.from_arrays(ref, tst, layout, ref_nodata, tst_nodata)
+    return compute_sam_sid_lmse_caseB_pair(pair, valid)
+
+
+def compute_sam_sid_lmse_caseB_pair(pair: DevicePair, valid=None) -> Dict[str, float]:
+    """SAM / SID / LMSE on a device-resident pair."""
     vdev = _valid_to_device(valid, pair.rows, pair.width, "Mask shape mismatch for Case B metrics")
     P = evaluate(pair, Want(stats=False, sam=True, sid=True, lmse=True), vdev)
     h = P.to_host()
@@ -185,14 +184,15 @@ def compute_sam_sid_lmse_caseB_arrays(ref, tst, valid=None, *, ref_nodata=None, 
 
 def compute_sam_sid_lmse_caseB(ref_path: Path, tst_path: Path, valid: Optional[np.ndarray] = None) -> Dict[str, float]:
     """Compute SAM (deg), SID, and LMSE for Case B (run_codec.py:308-347)."""
-    A, R, info = _read_pair(ref_path, tst_path)
+    from .ingest import load_pair
+    pair, info = load_pair(ref_path, tst_path)
     if valid is not None:
         if tuple(valid.shape) != (info["H"], info["W"]):
             raise ValueError("Mask shape mismatch for Case B metrics")
         m = valid                      # the dataset masks are NOT applied when `valid` is given (:314-319)
     else:
         m = _fold_masks(None, info)
-    return compute_sam_sid_lmse_caseB_arrays(A, R, m, ref_nodata=info["ref_nodata"], tst_nodata=info["tst_nodata"])
+    return compute_sam_sid_lmse_caseB_pair(pair, m)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -92,6 +92,12 @@ def error_max8_arrays(A, B, err_max_global=255, err_max_zoom=None, pct=(2, 98), 
     """
     assert tuple(A.shape) == tuple(B.shape), "Dims/band count must match"
     pair = DevicePair.from_arrays(A, B, layout, a_nodata, b_nodata)
+    return error_max8_pair(pair, err_max_global, err_max_zoom, pct, a_mask=a_mask, b_mask=b_mask)
+
+
+def error_max8_pair(pair: DevicePair, err_max_global=255, err_max_zoom=None, pct=(2, 98), *, a_mask=None,
+                    b_mask=None) -> Dict[str, object]:
+    """error_max8_arrays on a device-resident pair."""
     H, W = pair.rows, pair.width
     extra = None
     for m in (a_mask, b_mask):
@@ -189,13 +195,14 @@ def write_error_max8(a_path, b_path, out_path_base, err_max_global=255, err_max_
       - <base>_ERR8_0_<err_max_zoom>.tif (optional)
     Returns: (global_path, zoom_path or None)
     """
-    with open_raster(a_path) as a, open_raster(b_path) as b:
-        A = a.read()
-        B = b.read()
-        assert A.shape == B.shape, "Dims/band count must match"
-        res = error_max8_arrays(A, B, err_max_global, err_max_zoom, pct, a_nodata=a.nodata, b_nodata=b.nodata,
-                                a_mask=explicit_mask(a), b_mask=explicit_mask(b))
-        meta = a.meta.copy()
+    from .ingest import load_pair
+    if True:
+        try:
+            pair, info = load_pair(a_path, b_path)      # read once per rep, shared with compute_metrics
+        except AssertionError:
+            raise AssertionError("Dims/band count must match")
+        res = error_max8_pair(pair, err_max_global, err_max_zoom, pct, a_mask=info["ref_mask"], b_mask=info["tst_mask"])
+        meta = dict(info["ref_meta"])
         meta.update(driver="GTiff", count=1, dtype=uint8_dtype(), photometric="MINISBLACK", tiled=True,
                     blockxsize=512, blockysize=512, compress="DEFLATE")
         meta.pop("nodata", None)

@@ -426,3 +426,51 @@ def test_launcher_rebinds_the_reference_module(tmp_path):
     extra = mod.compute_sam_sid_lmse_caseB(Path("/mem/src.tif"), Path("/mem/recon.tif"), valid=None)
     for k, w in c["sam_sid_lmse"].items():
         assert _close(extra[k], w), k
+
+
+@pytest.mark.gpu
+def test_real_geotiff_files_read_once_per_rep(tmp_path, monkeypatch):
+    """The three drop-in calls of one rep (run_codec.py:518, :522, :526) on REAL files: built-in GeoTIFF
+    reader (no rasterio), pixel-interleaved cubes uploaded as stored (BIP), each file read ONCE."""
+    import sys
+    monkeypatch.delitem(sys.modules, "rasterio", raising=False)      # a stub another test may have installed
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import geotiff, ingest, quicklooks as ql
+    from oracle import distortion_oracle as orc
+    ref, dec = _rand_pair(31, "uint16", 8, 96, 80, 6, lowbits=2)
+    valid = np.random.default_rng(32).random((96, 80)) < 0.7
+    for name, cube in (("src.tif", ref), ("recon.tif", dec)):
+        with geotiff.open(tmp_path / name, "w", dtype="uint16", count=8, width=80, height=96, tiled=True,
+                          blockxsize=64, blockysize=64, compress="NONE" if name == "src.tif" else "DEFLATE") as dst:
+            dst.write(cube)
+    ingest.clear_cache()
+    r0 = ingest.STATS["reads"]
+    src, rec = tmp_path / "src.tif", tmp_path / "recon.tif"
+    og, oz = ql.write_error_max8(src, rec, tmp_path / "recon", err_max_global=255, err_max_zoom=32)
+    got = dm.compute_metrics(src, rec, valid=valid)
+    spec = dm.compute_sam_sid_lmse_caseB(src, rec, valid=valid)
+    assert ingest.STATS["reads"] - r0 == 2, "every file must be read exactly once for the three calls"
+    pair, _ = ingest.load_pair(src, rec)
+    assert pair.layout == "bip"
+    _check_metrics(got, orc.compute_metrics(ref, dec, valid, extras=False))
+    want = orc.compute_sam_sid_lmse_caseB(ref, dec, valid)
+    for k, w in want.items():
+        assert _close(spec[k], w), (k, spec[k], w)
+    o = orc.error_max8(ref, dec, 255, 32)
+    assert og.name == "recon_ERR8_0_255.tif" and oz.name == "recon_ERR8_0_32.tif"
+    with geotiff.open(og) as d:
+        assert np.array_equal(d.read(1), o["err8_g"]) and d.dtypes[0] == "uint8" and d.tiled
+        assert np.array_equal(d.dataset_mask(), np.full((96, 80), 255, np.uint8))
+    with geotiff.open(oz) as d:
+        assert np.array_equal(d.read(1), o["err8_z"])
+    tags = geotiff.read_tags(og)
+    assert tags["STATISTICS_MEAN"] == str(float(o["err8_g"].mean())) and tags["STATISTICS_MAXIMUM"] == "255"
+    # a new decode at the same path (next rep) must not be served from the cache
+    import os, time
+    dec2 = dec.copy(); dec2[0, 0, 0] ^= 0x100
+    with geotiff.open(rec, "w", dtype="uint16", count=8, width=80, height=96, compress="DEFLATE") as dst:
+        dst.write(dec2)
+    os.utime(rec, ns=(time.time_ns(), time.time_ns() + 1_000_000))
+    got2 = dm.compute_metrics(src, rec)
+    assert got2["max_abs_err"] == orc.compute_metrics(ref, dec2, extras=False)["max_abs_err"]
+    assert ingest.STATS["reads"] - r0 == 3
