@@ -8,9 +8,17 @@
 // border, so no boundary rule is needed.  The kernel filters x^2 + y^2 as ONE plane (only vx + vy
 // is used), i.e. four planes instead of five.
 //
-// Shared-memory tiled, separable: stage a (16+10) x (32+10) tile of both cubes, horizontal pass into
-// four float64 planes, vertical pass + SSIM formula + block-ordered partial sums.  FP64-FMA bound
-// (~130 DFMA per pixel), not HBM bound; see DESIGN.md.
+// Shared-memory tiled, separable, FP64-FMA bound (4 planes x 11 taps x 2 passes = 88 DFMA per pixel, so
+// <= ~0.55 TB/s of pair bytes at the measured 62.7 DFMA lanes/clk/SM); the tiling keeps everything else
+// off the FP64 pipe's back:
+//   stage   (54+10) x (32+10) samples of both cubes as int32 in shared memory
+//   pass H  a thread makes FOUR neighbouring outputs of one row: 14 inputs are converted to float64 and
+//           squared/multiplied ONCE (not once per tap), 176 DFMA, results to four float64 planes in
+//           shared memory; 64 rows x 8 groups = 512 items = exactly two per thread
+//   pass V  a thread makes SEVEN vertically neighbouring outputs of one column, plane by plane: 17
+//           shared-memory loads feed 77 DFMA (2.4 loads per output and plane instead of 11), then the
+//           SSIM formula; block-ordered partial sums
+// Column index is the fastest thread index in both passes, so shared-memory accesses are conflict free.
 
 #include <cmath>
 
@@ -21,17 +29,25 @@ namespace dm {
 namespace {
 
 constexpr int kSsimBlocks = 296;
-constexpr int SW = 32, SH = 16, RAD = 5;
+constexpr int SW = 32, SH = 54, RAD = 5;
+static_assert(SH + 2 * RAD == 64, "pass H decodes its item index with shifts");
+constexpr int IW = SW + 2 * RAD, IH = SH + 2 * RAD;     // 42 x 64 staged samples
+constexpr int VSEG = 7;                                 // outputs per thread in pass V (8 segments >= 54 rows)
+constexpr int HP = SW + 1;                              // row pitch of the float64 planes (odd: see pass H)
+constexpr int PH = IH + 2;                              // plane rows incl. two never-written rows that only
+                                                        // discarded outputs of the last segment read
+constexpr int kSsimSmem = 2 * IH * (IW + 1) * 4 + 4 * PH * HP * 8;
 
 struct Taps { double w[2 * RAD + 1]; };
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t band_stride, int64_t width,
                   int64_t r_lo, int64_t r_hi, int64_t buf_rows, Taps taps, double c1, double c2, double* out) {
-  __shared__ int xs[SH + 2 * RAD][SW + 2 * RAD + 1];
-  __shared__ int ys[SH + 2 * RAD][SW + 2 * RAD + 1];
-  __shared__ double hp[4][SH + 2 * RAD][SW];
+  extern __shared__ __align__(16) unsigned char ssim_smem[];
+  int (*xs)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem);
+  int (*ys)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem + IH * (IW + 1) * 4);
+  double (*hp)[PH][HP] = reinterpret_cast<double (*)[PH][HP]>(ssim_smem + 2 * IH * (IW + 1) * 4);   // [4][PH][HP]
   __shared__ double red[2][8];
   const int band = blockIdx.y;
   const T* A = ref + (int64_t)band * band_stride;
@@ -40,51 +56,90 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   const int64_t c_lo = RAD, c_hi = width - RAD;        // counted columns [c_lo, c_hi)
   const int64_t ncols = c_hi - c_lo, nrows = r_hi - r_lo;
   double acc = 0.0, cnt = 0.0;
+  // the window is symmetric: six distinct taps, kept in registers (indices are compile-time after unrolling)
+  double ws[RAD + 1];
+#pragma unroll
+  for (int k = 0; k <= RAD; ++k) ws[k] = taps.w[k];
+#define DM_TAP(k) ws[(k) <= RAD ? (k) : 2 * RAD - (k)]
   if (ncols > 0 && nrows > 0) {
     const int64_t tiles_x = (ncols + SW - 1) / SW, tiles_y = (nrows + SH - 1) / SH;
     const int64_t ntiles = tiles_x * tiles_y;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t r0 = r_lo + (t / tiles_x) * SH, c0 = c_lo + (t % tiles_x) * SW;
+      const int rows_here = (int)(r_hi - r0 < SH ? r_hi - r0 : SH), cols_here = (int)(c_hi - c0 < SW ? c_hi - c0 : SW);
       __syncthreads();
-      for (int i = threadIdx.x; i < (SH + 2 * RAD) * (SW + 2 * RAD); i += 256) {
-        const int lr = i / (SW + 2 * RAD), lc = i - lr * (SW + 2 * RAD);
-        int64_t r = r0 + lr - RAD, c = c0 + lc - RAD;
-        r = r < 0 ? 0 : (r >= buf_rows ? buf_rows - 1 : r);     // only reached by discarded outputs
-        c = c < 0 ? 0 : (c >= width ? width - 1 : c);
-        xs[lr][lc] = (int)A[r * width + c];
-        ys[lr][lc] = (int)R[r * width + c];
-      }
-      __syncthreads();
-      // horizontal pass: (SH+10) rows x SW columns
-      for (int i = threadIdx.x; i < (SH + 2 * RAD) * SW; i += 256) {
-        const int lr = i / SW, lc = i - lr * SW;
-        double hx = 0.0, hy = 0.0, hq = 0.0, hxy = 0.0;
-#pragma unroll
-        for (int k = 0; k <= 2 * RAD; ++k) {
-          const double x = (double)xs[lr][lc + k], y = (double)ys[lr][lc + k], w = taps.w[k];
-          hx = fma(w, x, hx); hy = fma(w, y, hy);
-          hq = fma(w, fma(x, x, y * y), hq); hxy = fma(w, x * y, hxy);
+      // stage: warp ty takes rows ty, ty+8, ...; lane = column (two columns for the first ten lanes).
+      // Clamped indices are only reached by outputs that are discarded.
+      {
+        int64_t ca = c0 + tx - RAD, cb = c0 + tx + 32 - RAD;
+        ca = ca < 0 ? 0 : (ca >= width ? width - 1 : ca);
+        cb = cb < 0 ? 0 : (cb >= width ? width - 1 : cb);
+#pragma unroll 4
+        for (int lr = ty; lr < IH; lr += 8) {
+          int64_t r = r0 + lr - RAD;
+          r = r < 0 ? 0 : (r >= buf_rows ? buf_rows - 1 : r);
+          const T* ar = A + r * width;
+          const T* rr = R + r * width;
+          xs[lr][tx] = (int)ar[ca];
+          ys[lr][tx] = (int)rr[ca];
+          if (tx < IW - 32) { xs[lr][tx + 32] = (int)ar[cb]; ys[lr][tx + 32] = (int)rr[cb]; }
         }
-        hp[0][lr][lc] = hx; hp[1][lr][lc] = hy; hp[2][lr][lc] = hq; hp[3][lr][lc] = hxy;
       }
       __syncthreads();
+      // ---- pass H: item = (group of 4 output columns, row lr); 512 items, two per thread.  The ROW is
+      // the fastest thread index: the lanes of a warp read the same columns of 32 rows (43 words apart)
+      // and write the same columns of 32 plane rows (33 doubles apart) -- both strides odd, conflict free.
+#pragma unroll 1
+      for (int item = threadIdx.x; item < IH * (SW / 4); item += 256) {
+        const int lr = item & (IH - 1), g4 = (item >> 6) * 4;
+        double vx[14], vy[14], vq[14], vp[14];
 #pragma unroll
-      for (int j = 0; j < SH; j += 8) {
-        const int lr = ty + j;
-        if (r0 + lr < r_hi && c0 + tx < c_hi) {
-          double ux = 0.0, uy = 0.0, uq = 0.0, uxy = 0.0;
+        for (int k = 0; k < 14; ++k) {
+          const double x = (double)xs[lr][g4 + k], y = (double)ys[lr][g4 + k];
+          vx[k] = x; vy[k] = y; vq[k] = fma(x, x, y * y); vp[k] = x * y;
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          double hx = 0.0, hy = 0.0, hq = 0.0, hxy = 0.0;
 #pragma unroll
           for (int k = 0; k <= 2 * RAD; ++k) {
-            const double w = taps.w[k];
-            ux = fma(w, hp[0][lr + k][tx], ux); uy = fma(w, hp[1][lr + k][tx], uy);
-            uq = fma(w, hp[2][lr + k][tx], uq); uxy = fma(w, hp[3][lr + k][tx], uxy);
+            const double w = DM_TAP(k);
+            hx = fma(w, vx[o + k], hx); hy = fma(w, vy[o + k], hy);
+            hq = fma(w, vq[o + k], hq); hxy = fma(w, vp[o + k], hxy);
           }
-          const double mm = ux * ux + uy * uy;
-          const double vsum = uq - mm, vxy = uxy - ux * uy;
-          const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
-          const double den = (mm + c1) * (vsum + c2);
-          acc += num / den;
-          cnt += 1.0;
+          hp[0][lr][g4 + o] = hx; hp[1][lr][g4 + o] = hy; hp[2][lr][g4 + o] = hq; hp[3][lr][g4 + o] = hxy;
+        }
+      }
+      __syncthreads();
+      // ---- pass V: thread = (column tx, rows 7*ty .. 7*ty+6), plane by plane
+      {
+        const int l0 = ty * VSEG;
+        double u[4][VSEG];
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+          double v[VSEG + 2 * RAD];
+#pragma unroll
+          for (int k = 0; k < VSEG + 2 * RAD; ++k) v[k] = hp[pl][l0 + k][tx];
+#pragma unroll
+          for (int o = 0; o < VSEG; ++o) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k <= 2 * RAD; ++k) s = fma(DM_TAP(k), v[o + k], s);
+            u[pl][o] = s;
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < VSEG; ++o) {
+          const int lr = l0 + o;
+          if (lr < rows_here && tx < cols_here) {
+            const double ux = u[0][o], uy = u[1][o], uq = u[2][o], uxy = u[3][o];
+            const double mm = ux * ux + uy * uy;
+            const double vsum = uq - mm, vxy = uxy - ux * uy;
+            const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
+            const double den = (mm + c1) * (vsum + c2);
+            acc += num / den;
+            cnt += 1.0;
+          }
         }
       }
     }
@@ -99,6 +154,8 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
     out[((int64_t)band * kSsimBlocks + blockIdx.x) * 2 + 1] = t1;
   }
 }
+
+#undef DM_TAP
 
 }  // namespace
 
@@ -124,8 +181,11 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
   const double c1 = (0.01 * L) * (0.01 * L), c2 = (0.03 * L) * (0.03 * L);
   const dim3 grid(kSsimBlocks, (unsigned)p.bands);
 #define DM_SSIM(T)                                                                                           \
-  ssim_gauss_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(p.ref), static_cast<const T*>(p.tst),      \
-                                            p.band_stride, p.width, r_lo, r_hi, p.rows, taps, c1, c2, out)
+  do {                                                                                                       \
+    DM_CUDA(cudaFuncSetAttribute(ssim_gauss_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsimSmem)); \
+    ssim_gauss_kernel<T><<<grid, 256, kSsimSmem, s>>>(static_cast<const T*>(p.ref), static_cast<const T*>(p.tst), \
+                                                      p.band_stride, p.width, r_lo, r_hi, p.rows, taps, c1, c2, out); \
+  } while (0)
   switch (p.dtype) {
     case DM_U8: DM_SSIM(uint8_t); break;
     case DM_U16: DM_SSIM(uint16_t); break;
