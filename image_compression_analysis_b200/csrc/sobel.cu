@@ -36,16 +36,21 @@ sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t r0 = row_begin + (t / tiles_x) * TH, c0 = (t % tiles_x) * TW;
     __syncthreads();
-    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
-      const int lr = i / (TW + 2), lc = i - lr * (TW + 2);
-      // np.pad(mode="edge"): clamp to the IMAGE, then map back to the buffer row
-      int64_t ir = img_row0 + r0 + lr - 1;
-      ir = ir < 0 ? 0 : (ir >= img_rows ? img_rows - 1 : ir);
-      int64_t c = c0 + lc - 1;
-      c = c < 0 ? 0 : (c >= width ? width - 1 : c);
-      const int64_t off = (ir - img_row0) * width + c;
-      sa[lr][lc] = (int)A[off];
-      sr[lr][lc] = (int)R[off];
+    // stage: warp ty takes rows ty, ty+8, ...; lane = column (lanes 0/1 also take columns 32/33).
+    // np.pad(mode="edge"): clamp to the IMAGE, then map back to the buffer row
+    {
+      int64_t ca = c0 + tx - 1, cb = c0 + tx + 32 - 1;
+      ca = ca < 0 ? 0 : (ca >= width ? width - 1 : ca);
+      cb = cb < 0 ? 0 : (cb >= width ? width - 1 : cb);
+      for (int lr = ty; lr < TH + 2; lr += 8) {
+        int64_t ir = img_row0 + r0 + lr - 1;
+        ir = ir < 0 ? 0 : (ir >= img_rows ? img_rows - 1 : ir);
+        const T* ar = A + (ir - img_row0) * width;
+        const T* rr = R + (ir - img_row0) * width;
+        sa[lr][tx] = (int)ar[ca];
+        sr[lr][tx] = (int)rr[ca];
+        if (tx < 2) { sa[lr][tx + 32] = (int)ar[cb]; sr[lr][tx + 32] = (int)rr[cb]; }
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -59,9 +64,10 @@ sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
           const int p00 = s[lr][tx], p01 = s[lr][tx + 1], p02 = s[lr][tx + 2];
           const int p10 = s[lr + 1][tx], p12 = s[lr + 1][tx + 2];
           const int p20 = s[lr + 2][tx], p21 = s[lr + 2][tx + 1], p22 = s[lr + 2][tx + 2];
-          const long long gx = (long long)(p00 - p02) + 2ll * (p10 - p12) + (p20 - p22);
-          const long long gy = (long long)(p00 - p20) + 2ll * (p01 - p21) + (p02 - p22);
-          mag[q] = __dsqrt_rn((double)(gx * gx + gy * gy));
+          const int gx = (p00 - p02) + 2 * (p10 - p12) + (p20 - p22);      // |g| <= 4*65535: int32
+          const int gy = (p00 - p20) + 2 * (p01 - p21) + (p02 - p22);
+          const double fx = (double)gx, fy = (double)gy;                   // exact; fx^2 + fy^2 < 2^38 exact
+          mag[q] = __dsqrt_rn(fma(fx, fx, fy * fy));
           s = sr;
         }
         const double e = __dsub_rn(mag[0], mag[1]);
