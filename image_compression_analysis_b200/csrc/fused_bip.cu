@@ -107,6 +107,10 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ uint32_t vmaxu2(uint32_t a, uint32_t b) { uint32_t r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t vminu2(uint32_t a, uint32_t b) { uint32_t r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -521,14 +525,15 @@ fused_bip_kernel(FusedArgs g) {
 // shared-memory totals, which also makes the end-of-kernel combine a plain per-band read.
 constexpr int kPixelWarpsCT = 8;
 constexpr int kPixelThreadsCT = kPixelWarpsCT * 32;
-template <int BANDS> struct Geo {
+template <int BANDS, int MPW_ = 4> struct Geo {
+  static constexpr int MPW = MPW_;                      // ldmatrix matrices (16-byte chunks) per band warp: 4 or 2
   static constexpr int W = BANDS / 2;                   // 32-bit words per pixel
   static constexpr int PIXB = BANDS * 2;                // bytes per pixel
   static constexpr int P = kTilePixels;                 // 64
   static constexpr int CUBE = P * PIXB;                 // one cube's share of a stage
   static constexpr int STAGE = 2 * CUBE;
   static constexpr int CHUNKS = BANDS / 4;              // 16-byte chunks per pixel pair
-  static constexpr int BAND_WARPS = (CHUNKS + 3) / 4, BAND_THREADS = BAND_WARPS * 32;   // 12 for 180 bands
+  static constexpr int BAND_WARPS = (CHUNKS + MPW - 1) / MPW, BAND_THREADS = BAND_WARPS * 32;   // 12 / 23 for 180 bands
   static constexpr int ROWBLOCKS = P / 16;              // ldmatrix row blocks (8 pixel pairs) per tile
   static constexpr int THREADS = BAND_THREADS + kPixelThreadsCT;   // 640: 20 warps x 96 registers
   static constexpr int CONSUMERS = BAND_WARPS + kPixelWarpsCT / 2;    // warps that read one tile
@@ -538,7 +543,8 @@ template <int BANDS> struct Geo {
   static_assert(BANDS % 4 == 0 && BANDS <= 256, "dp2a lo/hi pixel partials need B <= 256");
   static_assert(SMEM <= 227 * 1024, "ring does not fit");
   static_assert((PIXB / 8) % 2 == 1, "conflict-free LDS.64 / ldmatrix walks need an odd pixel pitch in 8-byte units");
-  static_assert(BAND_WARPS == 12, "the 20-warp layout (3 band + 2 pixel warps per scheduler) assumes 12 band warps");
+  static_assert(MPW == 2 || MPW == 4, "ldmatrix x2 / x4");
+  static_assert(THREADS <= 1024, "too many band warps for one CTA");
 };
 
 // barrier helpers on raw shared-memory addresses (computed once per thread, not per tile)
@@ -568,10 +574,10 @@ __device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
   return pending == 1u;
 }
 
-template <int BANDS, int DT, bool MASK, bool ERR>
-__global__ void __launch_bounds__(Geo<BANDS>::THREADS, 1)
+template <int BANDS, int DT, bool MASK, bool ERR, int MPW>
+__global__ void __launch_bounds__(Geo<BANDS, MPW>::THREADS, 1)
 fused_ct_kernel(FusedArgs g) {
-  using G = Geo<BANDS>;
+  using G = Geo<BANDS, MPW>;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
   __shared__ unsigned h8g[256], h8z[256];
@@ -644,21 +650,22 @@ fused_ct_kernel(FusedArgs g) {
     // different 16-byte bank groups (conflict free).
     const int ts = tid;
     const int c = lane >> 2, r = lane & 3;
-    const int nmat = (G::CHUNKS - 4 * warp) < 4 ? (G::CHUNKS - 4 * warp) : 4;     // >= 1 for every band warp
-    const int sc0 = 32 * warp + c;                     // sample column of matrix j: sc0 + 8j
+    const int nmat = (G::CHUNKS - MPW * warp) < MPW ? (G::CHUNKS - MPW * warp) : MPW;     // >= 1 for every band warp
+    const int sc0 = 8 * MPW * warp + c;                // sample column of matrix j: sc0 + 8j
     auto par_of = [&](int j) { return sc0 + 8 * j >= BANDS; };
     auto band_of = [&](int j) { const int sc = sc0 + 8 * j; return sc >= BANDS ? sc - BANDS : sc; };
-    const int mchunk = (4 * warp + (lane >> 3)) < G::CHUNKS ? (4 * warp + (lane >> 3)) : (G::CHUNKS - 1);
+    const int mlane = (lane >> 3) & (MPW - 1);
+    const int mchunk = (MPW * warp + mlane) < G::CHUNKS ? (MPW * warp + mlane) : (G::CHUNKS - 1);
     const uint32_t ld_off = ring + (uint32_t)(lane & 7) * (2u * G::PIXB) + (uint32_t)mchunk * 16u;
-    BandAccS a[4];
+    BandAccS a[MPW];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; a[j].zero = g.zero; }
+    for (int j = 0; j < MPW; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; a[j].zero = g.zero; }
     uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
     uint32_t n0 = 0, n1 = 0;                           // MASK: selected even / odd pixels of this thread's rows
 
     auto spill = [&]() {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < MPW; ++j) {
         if (j < nmat) {
           const int b = band_of(j);
           atomicAdd(tot + 0 * BANDS + b, (unsigned long long)a[j].sabs);
@@ -689,9 +696,14 @@ fused_ct_kernel(FusedArgs g) {
             const uint8_t* pl = MASK ? g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P : nullptr;
 #pragma unroll
             for (int rb = 0; rb < G::ROWBLOCKS; ++rb) {
-              uint32_t xr[4], yr[4];
-              ldsm_x4_trans(xr, xs + rb * (16 * G::PIXB));
-              ldsm_x4_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+              uint32_t xr[MPW], yr[MPW];
+              if constexpr (MPW == 4) {
+                ldsm_x4_trans(xr, xs + rb * (16 * G::PIXB));
+                ldsm_x4_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+              } else {
+                ldsm_x2_trans(xr, xs + rb * (16 * G::PIXB));
+                ldsm_x2_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+              }
               uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
               if (MASK) {
                 // pixels 16rb + 4r .. +3 of the tile: even/odd pixel of row 2r, even/odd pixel of row 2r+1
@@ -703,12 +715,16 @@ fused_ct_kernel(FusedArgs g) {
               }
               // data-range scan on the raw reference words (unmasked); a short last warp re-reads its
               // last chunk in the unused matrices, which changes neither an OR nor a maximum
-              orbits |= xr[0] | xr[1]; orbits |= xr[2] | xr[3];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { xr[j] ^= OFS; yr[j] ^= OFS; }
-              umax = __vimax3_u16x2(umax, xr[0], xr[1]); umax = __vimax3_u16x2(umax, xr[2], xr[3]);
-              if (DT == DM_I16) { umin = __vimin3_u16x2(umin, xr[0], xr[1]); umin = __vimin3_u16x2(umin, xr[2], xr[3]); }
-              if (!TRACK) { ymax = __vimax3_u16x2(ymax, yr[0], yr[1]); ymax = __vimax3_u16x2(ymax, yr[2], yr[3]); }
+              for (int j = 0; j < MPW; j += 2) orbits |= xr[j] | xr[j + 1];
+#pragma unroll
+              for (int j = 0; j < MPW; ++j) { xr[j] ^= OFS; yr[j] ^= OFS; }
+#pragma unroll
+              for (int j = 0; j < MPW; j += 2) {
+                umax = __vimax3_u16x2(umax, xr[j], xr[j + 1]);
+                if (DT == DM_I16) umin = __vimin3_u16x2(umin, xr[j], xr[j + 1]);
+                if (!TRACK) ymax = __vimax3_u16x2(ymax, yr[j], yr[j + 1]);
+              }
 #pragma unroll
               for (int j = 0; j < NM; ++j) {
                 uint32_t x = xr[j], y = yr[j];
@@ -728,15 +744,15 @@ fused_ct_kernel(FusedArgs g) {
         spill();
       }
     };
-    if (nmat == 4) run(std::integral_constant<int, 4>());
-    else if (nmat == 3) run(std::integral_constant<int, 3>());
-    else if (nmat == 2) run(std::integral_constant<int, 2>());
+    if (nmat == MPW) run(std::integral_constant<int, MPW>());
+    else if (MPW == 4 && nmat == 3) run(std::integral_constant<int, MPW == 4 ? 3 : 1>());
+    else if (MPW == 4 && nmat == 2) run(std::integral_constant<int, MPW == 4 ? 2 : 1>());
     else run(std::integral_constant<int, 1>());
 
     // ---- flush: per-band maxima and counts -> shared, then one thread per band -> global
     if (my_tiles > 0 && !(dbg & 2)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < MPW; ++j) {
         if (j < nmat) {
           atomicMax(tot_maxd + band_of(j), (unsigned)hmax2(a[j].maxd));
           if (MASK) atomicAdd(tot_n + band_of(j), (unsigned long long)(par_of(j) ? n1 : n0));
@@ -954,9 +970,9 @@ int run_generic(FusedArgs g, int dtype, cudaStream_t s) {
 }
 
 // compile-time geometry kernel over g.ntiles FULL tiles of 64 pixels
-template <int BANDS>
+template <int BANDS, int MPW>
 int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
-  using G = Geo<BANDS>;
+  using G = Geo<BANDS, MPW>;
   g.P = G::P; g.tail_pixels = 0;
   const int sms = sm_count();
   if (sms < 0) return DM_ECUDA;
@@ -964,7 +980,7 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
   if (grid > g.ntiles) grid = g.ntiles;
 #define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
   do {                                                                                                \
-    auto k = fused_ct_kernel<BANDS, DT, MASK, ERR>;                                                   \
+    auto k = fused_ct_kernel<BANDS, DT, MASK, ERR, MPW>;                                              \
     DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));      \
     k<<<(unsigned)grid, G::THREADS, G::SMEM, s>>>(g);                                                 \
   } while (0)
@@ -1014,7 +1030,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
     // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
     g.ntiles = g.npix / kTilePixels;
     const int64_t done = g.ntiles * kTilePixels;
-    int rc = run_ct<180>(g, p.dtype, s);
+    int rc = (g.debug & 16) ? run_ct<180, 2>(g, p.dtype, s) : run_ct<180, 4>(g, p.dtype, s);
     if (rc != DM_OK || done == g.npix) return rc;
     g.ref = static_cast<const char*>(g.ref) + done * B * 2;
     g.tst = static_cast<const char*>(g.tst) + done * B * 2;
