@@ -423,8 +423,9 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     # one-pass BIP kernel: stats + error planes + SAM from a single read (the plane selects METRICS
     # pixels for the stats and QUICKLOOK / SPECTRAL pixels for the rest, so it needs use == plane)
     # (for EnMAP's 180 bands it is also the fastest stats-only kernel: its pixel warps then idle)
-    if (want.stats and want.moments and not want.hist_bins and not want.generic_stats and not want.sid
-            and (want_planes or want.sam or pair.bands == 180) and pair.layout == "bip" and use is plane and want.fused):
+    if (want.stats and (want.moments or pair.bands == 180) and not want.hist_bins and not want.generic_stats
+            and not want.sid and (want_planes or want.sam or pair.bands == 180) and pair.layout == "bip"
+            and use is plane and want.fused):
         rc = L.dm_fused_bip(C.byref(cp), _ptr(plane), _ptr(P.sums), _ptr(P.imax), *spectral_args,
                             1 if want.sam else 0, _ptr(P.spec), _ptr(ws), st)
         if rc == _lib.DM_OK:
