@@ -1026,7 +1026,8 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
   if (g.npix <= 0) return DM_OK;
   const bool force_generic = (g.debug & 8) != 0;
-  if (B == 180 && g.npix >= kTilePixels && !force_generic) {
+  // (the specialised kernel reads four mask bytes at a time: the plane must be 4-byte aligned)
+  if (B == 180 && g.npix >= kTilePixels && !force_generic && !(reinterpret_cast<uintptr_t>(plane) & 3)) {
     // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
     g.ntiles = g.npix / kTilePixels;
     const int64_t done = g.ntiles * kTilePixels;
