@@ -190,37 +190,49 @@ class Reader:
     def _grid(self):
         return (self.width + self._bw - 1) // self._bw, (self.height + self._bh - 1) // self._bh
 
-    def read_native(self):
+    def native_shape(self):
+        """(shape, layout) of what read_native() returns."""
+        B, H, W = self.count, self.height, self.width
+        if self._planar == 1 and B > 1:
+            return (H, W, B), "bip"
+        return (B, H, W), "bsq"
+
+    def read_native(self, out: Optional[np.ndarray] = None, threads: int = 8):
         """All samples without de-interleaving: ((H,W,B) array, "bip") for chunky multi-band files,
-        ((B,H,W) array, "bsq") otherwise."""
+        ((B,H,W) array, "bsq") otherwise.  `out`: a caller buffer of native_shape() and the file's
+        dtype to decode into (e.g. pinned memory); blocks are decoded by a small thread pool
+        (zlib and the numpy copies release the GIL)."""
         nx, ny = self._grid()
         B, H, W = self.count, self.height, self.width
-        dt = self._dtype
-        if self._planar == 1:
-            out = np.empty((H, W, B), dt)
-            for by in range(ny):
-                y0 = by * self._bh
-                rows_in_file = self._bh if self.tiled else min(self._bh, H - y0)
-                for bx in range(nx):
-                    x0 = bx * self._bw
-                    blk = self._block(by * nx + bx, rows_in_file, self._bw, B)
-                    h, w = min(self._bh, H - y0), min(self._bw, W - x0)
-                    out[y0:y0 + h, x0:x0 + w, :] = blk[:h, :w, :]
-            if B == 1:
-                return out.reshape(H, W)[None], "bsq"
-            return out, "bip"
-        out = np.empty((B, H, W), dt)
+        shape, layout = self.native_shape()
+        if out is None:
+            out = np.empty(shape, self._dtype)
+        elif tuple(out.shape) != shape or out.dtype != self._dtype:
+            raise ValueError(f"read_native: out must be {shape} {self._dtype}, not {out.shape} {out.dtype}")
+        chunky = self._planar == 1
+        view = out.reshape(H, W, B) if (chunky and B == 1) else out       # (1,H,W) == (H,W,1) in memory
         per_band = nx * ny
-        for b in range(B):
-            for by in range(ny):
-                y0 = by * self._bh
-                rows_in_file = self._bh if self.tiled else min(self._bh, H - y0)
-                for bx in range(nx):
-                    x0 = bx * self._bw
-                    blk = self._block(b * per_band + by * nx + bx, rows_in_file, self._bw, 1)
-                    h, w = min(self._bh, H - y0), min(self._bw, W - x0)
-                    out[b, y0:y0 + h, x0:x0 + w] = blk[:h, :w, 0]
-        return out, "bsq"
+
+        def job(k: int) -> None:
+            b, rest = (0, k) if chunky else divmod(k, per_band)
+            by, bx = divmod(rest, nx)
+            y0, x0 = by * self._bh, bx * self._bw
+            rows_in_file = self._bh if self.tiled else min(self._bh, H - y0)
+            h, w = min(self._bh, H - y0), min(self._bw, W - x0)
+            if chunky:
+                view[y0:y0 + h, x0:x0 + w, :] = self._block(k, rows_in_file, self._bw, B)[:h, :w, :]
+            else:
+                view[b, y0:y0 + h, x0:x0 + w] = self._block(k, rows_in_file, self._bw, 1)[:h, :w, 0]
+
+        nblocks = per_band if chunky else per_band * B
+        if threads > 1 and nblocks > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(threads, nblocks)) as ex:
+                list(ex.map(job, range(nblocks)))
+        else:
+            for k in range(nblocks):
+                job(k)
+        return out, layout
 
     def read(self, indexes=None, out_dtype=None):
         """rasterio semantics: read() -> (B,H,W); read(i) -> (H,W); read([i,j]) -> (k,H,W); 1-based."""

@@ -82,19 +82,25 @@ def load_cube(path) -> Cube:
         B, H, W = int(ds.count), int(ds.height), int(ds.width)
         name = np.dtype(ds.dtypes[0]).name
         dtype_code(name)
+        tdt = torch.int16 if np.dtype(name).itemsize == 2 else torch.uint8
         if hasattr(ds, "read_native"):
-            arr, layout = ds.read_native()
+            # the built-in reader decodes straight into the pinned staging buffer
+            shape, layout = ds.native_shape()
+            nbytes = int(np.prod(shape)) * np.dtype(name).itemsize
+            stage = _staging(nbytes)
+            # the staging buffer is reused by the next read: wait for the previous upload before overwriting it
+            torch.cuda.current_stream().synchronize()
+            host = stage[:nbytes].view(tdt).view(shape)
+            ds.read_native(out=host.numpy().view(np.dtype(name)))
         else:
-            arr, layout = ds.read(), "bsq"
+            arr, layout = np.ascontiguousarray(ds.read()), "bsq"
+            if arr.dtype == np.uint16:
+                arr = arr.view(np.int16)
+            stage = _staging(arr.nbytes)
+            torch.cuda.current_stream().synchronize()
+            host = stage[:arr.nbytes].view(tdt).view(arr.shape)
+            host.numpy()[...] = arr
         nodata, mask, meta = ds.nodata, explicit_mask(ds), ds.meta.copy()
-    a = np.ascontiguousarray(arr)
-    if a.dtype == np.uint16:
-        a = a.view(np.int16)
-    stage = _staging(a.nbytes)
-    host = stage[:a.nbytes].view(torch.int16 if a.dtype.itemsize == 2 else torch.uint8).view(a.shape)
-    # the staging buffer is reused by the next read: wait for the previous upload before overwriting it
-    torch.cuda.current_stream().synchronize()
-    host.numpy()[...] = a
     t = host.to(dev, non_blocking=True)
     cube = Cube(t, name, layout, B, H, W, nodata, mask, meta)
     if key is not None:
