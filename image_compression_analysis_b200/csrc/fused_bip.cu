@@ -532,6 +532,7 @@ template <int BANDS, int MPW_ = 4> struct Geo {
   static constexpr int P = kTilePixels;                 // 64
   static constexpr int CUBE = P * PIXB;                 // one cube's share of a stage
   static constexpr int STAGE = 2 * CUBE;
+  static constexpr int PITCH = STAGE + 128;             // a stage in the ring: both cubes' tiles + the tile's mask bytes
   static constexpr int CHUNKS = BANDS / 4;              // 16-byte chunks per pixel pair
   static constexpr int BAND_WARPS = (CHUNKS + MPW - 1) / MPW, BAND_THREADS = BAND_WARPS * 32;   // 12 / 23 for 180 bands
   static constexpr int ROWBLOCKS = P / 16;              // ldmatrix row blocks (8 pixel pairs) per tile
@@ -539,13 +540,18 @@ template <int BANDS, int MPW_ = 4> struct Geo {
   static constexpr int CONSUMERS = BAND_WARPS + kPixelWarpsCT / 2;    // warps that read one tile
   static constexpr int NQ = 6;                          // abs, x, y, xx, yy, xy
   static constexpr size_t TOT_BYTES = (size_t)(NQ + 1) * BANDS * 8 + (size_t)BANDS * 4;   // totals, N, max|d|
-  static constexpr size_t SMEM = (size_t)kStages * STAGE + TOT_BYTES;
+  static constexpr size_t SMEM = (size_t)kStages * PITCH + TOT_BYTES;
   static_assert(BANDS % 4 == 0 && BANDS <= 256, "dp2a lo/hi pixel partials need B <= 256");
   static_assert(SMEM <= 227 * 1024, "ring does not fit");
   static_assert((PIXB / 8) % 2 == 1, "conflict-free LDS.64 / ldmatrix walks need an odd pixel pitch in 8-byte units");
   static_assert(MPW == 2 || MPW == 4, "ldmatrix x2 / x4");
   static_assert(THREADS <= 1024, "too many band warps for one CTA");
 };
+
+// signed dp2a for int16 samples: a = two s16, selector bytes unsigned (low bytes) / signed (high bytes)
+__device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t a, uint32_t b, uint32_t c) { int r; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"((int)c)); return (uint32_t)r; }
+__device__ __forceinline__ uint32_t dp2a_hi_ss(uint32_t a, uint32_t b, uint32_t c) { int r; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"((int)c)); return (uint32_t)r; }
+__device__ __forceinline__ uint32_t vadd2_wrap(uint32_t a, uint32_t b) { return __vadd2(a, b); }   // per-half add, VIADD.16x2
 
 // barrier helpers on raw shared-memory addresses (computed once per thread, not per tile)
 constexpr unsigned kPollNs = DM_POLL_NS;
@@ -583,7 +589,7 @@ fused_ct_kernel(FusedArgs g) {
   __shared__ unsigned h8g[256], h8z[256];
   __shared__ double red[3][kPixelWarpsCT];
   __shared__ int sh_cube[8];
-  unsigned long long* tot = reinterpret_cast<unsigned long long*>(smem + (size_t)kStages * G::STAGE);   // [NQ][BANDS]
+  unsigned long long* tot = reinterpret_cast<unsigned long long*>(smem + (size_t)kStages * G::PITCH);   // [NQ][BANDS]
   unsigned long long* tot_n = tot + G::NQ * BANDS;                                                      // [BANDS]
   unsigned* tot_maxd = reinterpret_cast<unsigned*>(tot_n + BANDS);                                      // [BANDS]
 
@@ -616,10 +622,12 @@ fused_ct_kernel(FusedArgs g) {
     uint64_t* fb = &full_bar[s];
     if (dbg & 1) { mbar_arrive(fb); return; }
     const int64_t off = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)G::CUBE;
-    unsigned char* dst = smem + (size_t)s * G::STAGE;
-    mbar_expect_tx(fb, G::STAGE);
+    unsigned char* dst = smem + (size_t)s * G::PITCH;
+    mbar_expect_tx(fb, G::STAGE + (MASK ? G::P : 0));
     bulk_g2s(dst, static_cast<const char*>(g.ref) + off, G::CUBE, fb);
     bulk_g2s(dst + G::CUBE, static_cast<const char*>(g.tst) + off, G::CUBE, fb);
+    // the tile's validity bytes ride along, so that no consumer touches global memory in its loop
+    if (MASK) bulk_g2s(dst + G::STAGE, g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P, G::P, fb);
   };
   // Called by lane 0 of a consumer warp when the warp has finished reading tile `it`.  There is no
   // producer warp: every consumer warp arrives on the stage's empty barrier, and the one whose arrival
@@ -660,7 +668,7 @@ fused_ct_kernel(FusedArgs g) {
     BandAccS a[MPW];
 #pragma unroll
     for (int j = 0; j < MPW; ++j) { a[j].sabs = a[j].sx = a[j].sy = a[j].xxl = a[j].xxh = a[j].yyl = a[j].yyh = a[j].xyl = a[j].xyh = a[j].maxd = 0; a[j].zero = g.zero; }
-    uint32_t maxsel_u = 0, maxsel_s = 0, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
+    uint32_t maxsel_u = 0, minsel_m1 = 0xffffffffu, umax = 0, umin = 0xffffffffu, orbits = 0, ymax = 0;
     uint32_t n0 = 0, n1 = 0;                           // MASK: selected even / odd pixels of this thread's rows
 
     auto spill = [&]() {
@@ -692,8 +700,8 @@ fused_ct_kernel(FusedArgs g) {
           const int s = it & (kStages - 1);
           mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
           if (!(dbg & 2)) {
-            const uint32_t xs = ld_off + (uint32_t)s * G::STAGE;
-            const uint8_t* pl = MASK ? g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P : nullptr;
+            const uint32_t xs = ld_off + (uint32_t)s * G::PITCH;
+            const unsigned char* pl = smem + (size_t)s * G::PITCH + G::STAGE;      // MASK: the tile's validity bytes
 #pragma unroll
             for (int rb = 0; rb < G::ROWBLOCKS; ++rb) {
               uint32_t xr[MPW], yr[MPW];
@@ -729,12 +737,13 @@ fused_ct_kernel(FusedArgs g) {
               for (int j = 0; j < NM; ++j) {
                 uint32_t x = xr[j], y = yr[j];
                 if (MASK) { const uint32_t m = par_of(j) ? m1 : m0; x &= m; y &= m; }
-                if (DT == DM_I16) {
-                  // np.abs semantics on the signed samples (wrapping abs of -32768 never wins)
-                  const uint32_t mm = MASK ? (par_of(j) ? m1 : m0) : 0xffffffffu;
-                  maxsel_s = __vimax3_s16x2(maxsel_s, __vabs2((x ^ OFS) & mm), __vabs2((y ^ OFS) & mm));
-                }
                 band_word<true, TRACK>(a[j], x, y, maxsel_u);
+                if (DT == DM_I16) {
+                  // max |v| with np.abs semantics (abs(-32768) wraps and never wins) from offset-binary
+                  // extremes: maxsel_u tracks max u (in band_word); here min over u > 0 as min of u-1
+                  // with per-half wrap (u = 0, i.e. -32768 or a masked sample, becomes 0xffff and drops out)
+                  minsel_m1 = vminu2(minsel_m1, vadd2_wrap(vminu2(x, y), 0xffffffffu));
+                }
               }
             }
           }
@@ -759,7 +768,12 @@ fused_ct_kernel(FusedArgs g) {
         }
       }
       if (!TRACK) maxsel_u = vmaxu2(umax, ymax);       // unmasked uint16: max over everything read
-      atomicMax(sh_cube + 0, DT == DM_I16 ? hmax2s(maxsel_s) : hmax2(maxsel_u));
+      if (DT == DM_I16) {
+        const int hi = hmax2(maxsel_u) - 32768, lo = 32768 - (hmin2(minsel_m1) + 1);   // lo = -32768 when no u > 0
+        atomicMax(sh_cube + 0, max(hi, lo));
+      } else {
+        atomicMax(sh_cube + 0, hmax2(maxsel_u));
+      }
       atomicMax(sh_cube + 1, hmax2(umax));
       atomicMin(sh_cube + 2, hmin2(umin));
       atomicOr(reinterpret_cast<unsigned*>(sh_cube + 3), (orbits | (orbits >> 16)) & 0xffffu);
@@ -819,12 +833,13 @@ fused_ct_kernel(FusedArgs g) {
     constexpr int H0 = (U + 1) / 2, H1 = U - H0;      // units of half 0 / half 1
     const unsigned char* lane_base = smem + (size_t)tp * G::PIXB + (hl ? H0 * 8 : 0);
     double s_acos = 0.0, s_n = 0.0;
-    uint32_t k_xxl = 0, k_xxh = 0, k_yyl = 0, k_yyh = 0, k_xyl = 0, k_xyh = 0, k_sx = 0, k_sy = 0, k_e = 0;
+    uint32_t k_xxl = 0, k_xxh = 0, k_yyl = 0, k_yyh = 0, k_xyl = 0, k_xyh = 0, k_e = 0;
     int k_it = 0;
+    uint32_t k_v = 0xff;
 
     auto finish = [&]() {
       const int64_t p = ((int64_t)blockIdx.x + (int64_t)k_it * gridDim.x) * G::P + tp;
-      const uint8_t v = MASK ? g.plane[p] : (uint8_t)0xff;
+      const uint32_t v = k_v;
       if (ERR) {
         int e = (v & DM_VALID_QUICKLOOK) ? hmax2(k_e) : 0;             // quicklooks.py:134
         if (g.errmax) g.errmax[p] = (uint16_t)e;
@@ -841,14 +856,15 @@ fused_ct_kernel(FusedArgs g) {
       }
       if (g.want_sam && (v & DM_VALID_SPECTRAL)) {
         // lo + 256*hi: both halves < 2^32 and the sum < 2^53, so float64 holds it exactly
-        double na2 = fma((double)k_xxh, 256.0, (double)k_xxl);
-        double nr2 = fma((double)k_yyh, 256.0, (double)k_yyl);
-        double dot = fma((double)k_xyh, 256.0, (double)k_xyl);
-        if (DT == DM_I16) {
-          const double c = 32768.0, c2B = 32768.0 * 32768.0 * (double)BANDS, fx = (double)k_sx, fy = (double)k_sy;
-          dot = dot - c * (fx + fy) + c2B;             // all terms exact integers below 2^53
-          na2 = na2 - 2.0 * c * fx + c2B;
-          nr2 = nr2 - 2.0 * c * fy + c2B;
+        double na2, nr2, dot;
+        if (DT == DM_I16) {                            // signed 32-bit partials
+          na2 = fma((double)(int)k_xxh, 256.0, (double)(int)k_xxl);
+          nr2 = fma((double)(int)k_yyh, 256.0, (double)(int)k_yyl);
+          dot = fma((double)(int)k_xyh, 256.0, (double)(int)k_xyl);
+        } else {
+          na2 = fma((double)k_xxh, 256.0, (double)k_xxl);
+          nr2 = fma((double)k_yyh, 256.0, (double)k_yyl);
+          dot = fma((double)k_xyh, 256.0, (double)k_xyl);
         }
         const double na = __dadd_rn(__dsqrt_rn(na2), 1e-12);
         const double nr = __dadd_rn(__dsqrt_rn(nr2), 1e-12);
@@ -863,23 +879,31 @@ fused_ct_kernel(FusedArgs g) {
     for (int it = grp; it < my_tiles; it += 2, ++visit) {
       const int s = it & (kStages - 1);
       mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
-      uint32_t emax = 0;
-      uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0, sx = 0, sy = 0;
+      uint32_t emax = 0, vcur = 0xff;
+      uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0;
       if (!(dbg & 4)) {
-        const unsigned char* xs = lane_base + (size_t)s * G::STAGE;
+        const unsigned char* xs = lane_base + (size_t)s * G::PITCH;
+        if (MASK) vcur = smem[(size_t)s * G::PITCH + G::STAGE + tp];
         auto unit = [&](int j) {
           const uint2 xv = *reinterpret_cast<const uint2*>(xs + 8 * j);
           const uint2 yv = *reinterpret_cast<const uint2*>(xs + G::CUBE + 8 * j);
-          const uint32_t xw[2] = {xv.x ^ OFS, xv.y ^ OFS}, yw[2] = {yv.x ^ OFS, yv.y ^ OFS};
+          const uint32_t xw[2] = {xv.x, xv.y}, yw[2] = {yv.x, yv.y};
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint32_t x = xw[k], y = yw[k];
-            if (ERR) emax = vmaxu2(emax, vmaxu2(x, y) - vminu2(x, y));
+            if (ERR) { const uint32_t ux = x ^ OFS, uy = y ^ OFS; emax = vmaxu2(emax, vmaxu2(ux, uy) - vminu2(ux, uy)); }
             const uint32_t px = __byte_perm(x, 0, 0x3120), py = __byte_perm(y, 0, 0x3120);
-            xxl = dp2a_lo(x, px, xxl); xxh = dp2a_hi(x, px, xxh);
-            yyl = dp2a_lo(y, py, yyl); yyh = dp2a_hi(y, py, yyh);
-            xyl = dp2a_lo(x, py, xyl); xyh = dp2a_hi(x, py, xyh);
-            if (DT == DM_I16) { sx = dp2a_lo(x, 0x0101u, sx); sy = dp2a_lo(y, 0x0101u, sy); }
+            if (DT == DM_I16) {
+              // signed samples directly: s16 x (unsigned low byte) and s16 x (signed high byte); a pixel's
+              // partials stay below 2^31 up to 256 bands (2 * 32768 * 255 per dp2a)
+              xxl = dp2a_lo_su(x, px, xxl); xxh = dp2a_hi_ss(x, px, xxh);
+              yyl = dp2a_lo_su(y, py, yyl); yyh = dp2a_hi_ss(y, py, yyh);
+              xyl = dp2a_lo_su(x, py, xyl); xyh = dp2a_hi_ss(x, py, xyh);
+            } else {
+              xxl = dp2a_lo(x, px, xxl); xxh = dp2a_hi(x, px, xxh);
+              yyl = dp2a_lo(y, py, yyl); yyh = dp2a_hi(y, py, yyh);
+              xyl = dp2a_lo(x, py, xyl); xyh = dp2a_hi(x, py, xyh);
+            }
           }
         };
 #pragma unroll 11
@@ -893,11 +917,10 @@ fused_ct_kernel(FusedArgs g) {
         xxl += __shfl_xor_sync(0xffffffffu, xxl, 16); xxh += __shfl_xor_sync(0xffffffffu, xxh, 16);
         yyl += __shfl_xor_sync(0xffffffffu, yyl, 16); yyh += __shfl_xor_sync(0xffffffffu, yyh, 16);
         xyl += __shfl_xor_sync(0xffffffffu, xyl, 16); xyh += __shfl_xor_sync(0xffffffffu, xyh, 16);
-        if (DT == DM_I16) { sx += __shfl_xor_sync(0xffffffffu, sx, 16); sy += __shfl_xor_sync(0xffffffffu, sy, 16); }
         if (ERR) emax = vmaxu2(emax, __shfl_xor_sync(0xffffffffu, emax, 16));
         if (hl == (visit & 1)) {
-          k_xxl = xxl; k_xxh = xxh; k_yyl = yyl; k_yyh = yyh; k_xyl = xyl; k_xyh = xyh; k_sx = sx; k_sy = sy; k_e = emax;
-          k_it = it;
+          k_xxl = xxl; k_xxh = xxh; k_yyl = yyl; k_yyh = yyh; k_xyl = xyl; k_xyh = xyh; k_e = emax;
+          k_it = it; k_v = vcur;
         }
         if (visit & 1) finish();
       }
@@ -917,6 +940,115 @@ fused_ct_kernel(FusedArgs g) {
       if (g.hist8_g && h8g[i]) atomic_add_i64(g.hist8_g + i, h8g[i]);
       if (g.hist8_z && h8z[i]) atomic_add_i64(g.hist8_z + i, h8z[i]);
     }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Validity plane of a 180-band BIP pair at HBM speed (the pre-pass of the nodata / caller-mask path,
+// run_codec.py:249-263, quicklooks.py:35-45, run_codec.py:314-319).  Same TMA ring and tile walk as
+// the pixel group above: two lanes per pixel OR / MIN the words of their half of the spectrum XORed
+// with the packed nodata value -- OR != 0 <=> some band differs from nodata (dataset_mask), MIN != 0
+// per half-word <=> no band equals it (the all-bands test).  Only cubes that have a nodata value are
+// read at all.
+struct ValArgs {
+  const void* ref;
+  const void* tst;
+  const uint8_t* valid_in;    // may be null
+  uint8_t* plane;
+  int64_t* counts;            // may be null
+  int64_t ntiles;
+  int ref_has, ref_nd, tst_has, tst_nd;
+  uint32_t poll_ns;
+};
+
+template <int BANDS>
+__global__ void __launch_bounds__(kPixelThreadsCT, 1)
+validity_ct_kernel(ValArgs g) {
+  using G = Geo<BANDS, 4>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kPixelWarpsCT / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_tiles = (int64_t)blockIdx.x < g.ntiles ? (int)((g.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
+  const uint32_t poll_ns = g.poll_ns;
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t tx_bytes = (g.ref_has ? G::CUBE : 0) + (g.tst_has ? G::CUBE : 0);
+
+  auto issue_tile = [&](int it) {
+    if (it >= my_tiles) return;
+    const int s = it & (kStages - 1);
+    uint64_t* fb = &full_bar[s];
+    const int64_t off = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)G::CUBE;
+    unsigned char* dst = smem + (size_t)s * G::STAGE;
+    mbar_expect_tx(fb, tx_bytes);
+    if (g.ref_has) bulk_g2s(dst, static_cast<const char*>(g.ref) + off, G::CUBE, fb);
+    if (g.tst_has) bulk_g2s(dst + G::CUBE, static_cast<const char*>(g.tst) + off, G::CUBE, fb);
+  };
+  auto release_tile = [&](int it) {
+    const uint32_t eb = empty0 + 8u * (uint32_t)(it & (kStages - 1));
+    if (mbar_arrive_is_last_a(eb)) {
+      mbar_wait_a(eb, (uint32_t)((it / kStages) & 1), poll_ns);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue_tile(it + kStages);
+    }
+  };
+  if (tid == 0) {
+    for (int it = 0; it < kStages; ++it) issue_tile(it);
+  }
+  const int grp = tid >> 7, wq = (tid >> 5) & 3, hl = lane >> 4;
+  const int tp = 16 * wq + (lane & 15);
+  constexpr int U = G::W / 2, H0 = (U + 1) / 2, H1 = U - H0;
+  const unsigned char* lane_base = smem + (size_t)tp * G::PIXB + (hl ? H0 * 8 : 0);
+  const uint32_t ndr = ((uint32_t)g.ref_nd & 0xffffu) * 0x10001u, ndt = ((uint32_t)g.tst_nd & 0xffffu) * 0x10001u;
+  int c0 = 0, c1 = 0, c2 = 0;
+  for (int it = grp; it < my_tiles; it += 2) {
+    const int s = it & (kStages - 1);
+    mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
+    const unsigned char* xs = lane_base + (size_t)s * G::STAGE;
+    uint32_t r_or = 0, r_min = 0xffffffffu, t_or = 0, t_min = 0xffffffffu, r_b1 = 1, t_b1 = 1;
+    auto scan = [&](const unsigned char* base, uint32_t nd2, uint32_t& o, uint32_t& m) {
+      auto unit = [&](int j) {
+        const uint2 v = *reinterpret_cast<const uint2*>(base + 8 * j);
+        const uint32_t a = v.x ^ nd2, b = v.y ^ nd2;
+        o |= a | b;
+        m = __vimin3_u16x2(m, a, b);
+      };
+#pragma unroll 11
+      for (int j = 0; j < H1; ++j) unit(j);
+      if (H0 > H1 && hl == 0) unit(H1);
+    };
+    if (g.ref_has) { scan(xs, ndr, r_or, r_min); r_b1 = ((*reinterpret_cast<const uint32_t*>(xs) ^ ndr) & 0xffffu) != 0; }
+    if (g.tst_has) { scan(xs + G::CUBE, ndt, t_or, t_min); t_b1 = ((*reinterpret_cast<const uint32_t*>(xs + G::CUBE) ^ ndt) & 0xffffu) != 0; }
+    __syncwarp();
+    if (lane == 0) release_tile(it);
+    r_or |= __shfl_xor_sync(0xffffffffu, r_or, 16); t_or |= __shfl_xor_sync(0xffffffffu, t_or, 16);
+    r_min = vminu2(r_min, __shfl_xor_sync(0xffffffffu, r_min, 16));
+    t_min = vminu2(t_min, __shfl_xor_sync(0xffffffffu, t_min, 16));
+    if (hl == 0) {                                     // lanes 0-15 hold band 1 and write the pixel
+      const int64_t p = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P + tp;
+      const bool ra = g.ref_has ? r_or != 0 : true, ta = g.tst_has ? t_or != 0 : true;
+      const bool rl = g.ref_has ? hmin2(r_min) != 0 : true, tl = g.tst_has ? hmin2(t_min) != 0 : true;
+      const bool vin = g.valid_in ? g.valid_in[p] != 0 : true;
+      const bool ds = ra && ta;
+      uint8_t v = 0;
+      if (ds && rl && tl && vin) v |= DM_VALID_METRICS;
+      if (ds && r_b1 && t_b1) v |= DM_VALID_QUICKLOOK;
+      if (g.valid_in ? vin : ds) v |= DM_VALID_SPECTRAL;
+      g.plane[p] = v;
+      c0 += (v & DM_VALID_METRICS) ? 1 : 0;
+      c1 += (v & DM_VALID_QUICKLOOK) ? 1 : 0;
+      c2 += (v & DM_VALID_SPECTRAL) ? 1 : 0;
+    }
+  }
+  const long long s0 = warp_sum_ll(c0), s1 = warp_sum_ll(c1), s2 = warp_sum_ll(c2);
+  if (lane == 0 && g.counts) {
+    if (s0) atomic_add_i64(g.counts + 0, s0);
+    if (s1) atomic_add_i64(g.counts + 1, s1);
+    if (s2) atomic_add_i64(g.counts + 2, s2);
   }
 }
 
@@ -1026,8 +1158,8 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
   if (g.npix <= 0) return DM_OK;
   const bool force_generic = (g.debug & 8) != 0;
-  // (the specialised kernel reads four mask bytes at a time: the plane must be 4-byte aligned)
-  if (B == 180 && g.npix >= kTilePixels && !force_generic && !(reinterpret_cast<uintptr_t>(plane) & 3)) {
+  // (the specialised kernel bulk-copies the tile's 64 mask bytes: the plane must be 16-byte aligned)
+  if (B == 180 && g.npix >= kTilePixels && !force_generic && !(reinterpret_cast<uintptr_t>(plane) & 15)) {
     // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
     g.ntiles = g.npix / kTilePixels;
     const int64_t done = g.ntiles * kTilePixels;
@@ -1042,6 +1174,36 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
     g.npix -= done;
   }
   return run_generic(g, p.dtype, s);
+}
+
+// full 64-pixel tiles of a 180-band, 16-bit BIP pair through validity_ct_kernel; returns the number of
+// pixels covered (0 when the geometry does not qualify: the caller then runs the generic kernel on everything)
+int64_t launch_validity_ct(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts,
+                           cudaStream_t s, int* status) {
+  *status = DM_OK;
+  const int64_t npix = p.rows * p.width;
+  if (p.layout != DM_BIP || p.bands != 180 || (p.dtype != DM_U16 && p.dtype != DM_I16) || npix < kTilePixels) return 0;
+  if ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 15) return 0;
+  if (!p.ref_has_nodata && !p.tst_has_nodata) return 0;          // nothing to read: the generic kernel is a plain fill
+  using G = Geo<180, 4>;
+  ValArgs g;
+  g.ref = p.ref; g.tst = p.tst; g.valid_in = valid_in; g.plane = plane_out; g.counts = counts;
+  g.ntiles = npix / kTilePixels;
+  g.ref_has = p.ref_has_nodata; g.ref_nd = p.ref_nodata; g.tst_has = p.tst_has_nodata; g.tst_nd = p.tst_nodata;
+  { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
+  const int sms = sm_count();
+  if (sms < 0) { *status = DM_ECUDA; return 0; }
+  int64_t grid = sms;
+  if (grid > g.ntiles) grid = g.ntiles;
+  const size_t smem = (size_t)kStages * G::STAGE;
+  auto k = validity_ct_kernel<180>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { *status = cuda_fail(e, "cudaFuncSetAttribute(validity_ct)"); return 0; }
+  k<<<(unsigned)grid, kPixelThreadsCT, smem, s>>>(g);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *status = cuda_fail(e, "validity_ct"); return 0; }
+  return g.ntiles * kTilePixels;
 }
 
 }  // namespace dm

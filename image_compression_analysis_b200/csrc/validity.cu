@@ -125,10 +125,26 @@ int launch_validity(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_
   if (p.bands <= 0 || p.rows < 0 || p.width < 0) return fail(DM_EARG, "dm_validity: bad geometry");
   if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_validity: bad layout");
   if (p.rows * p.width == 0) return DM_OK;
-  switch (p.dtype) {
-    case DM_U8: return run_validity<uint8_t>(p, valid_in, plane_out, counts, s);
-    case DM_U16: return run_validity<uint16_t>(p, valid_in, plane_out, counts, s);
-    case DM_I16: return run_validity<int16_t>(p, valid_in, plane_out, counts, s);
+  // EnMAP BIP cubes: full 64-pixel tiles through the TMA-staged kernel, the rest through the generic one
+  dm_pair_t q = p;
+  {
+    int st = DM_OK;
+    const int64_t done = launch_validity_ct(p, valid_in, plane_out, counts, s, &st);
+    if (st != DM_OK) return st;
+    if (done == p.rows * p.width) return DM_OK;
+    if (done > 0) {
+      const int64_t eb = 2;
+      q.ref = static_cast<const char*>(p.ref) + done * p.bands * eb;
+      q.tst = static_cast<const char*>(p.tst) + done * p.bands * eb;
+      q.rows = 1; q.width = p.rows * p.width - done;
+      if (valid_in) valid_in += done;
+      plane_out += done;
+    }
+  }
+  switch (q.dtype) {
+    case DM_U8: return run_validity<uint8_t>(q, valid_in, plane_out, counts, s);
+    case DM_U16: return run_validity<uint16_t>(q, valid_in, plane_out, counts, s);
+    case DM_I16: return run_validity<int16_t>(q, valid_in, plane_out, counts, s);
   }
   return fail(DM_EARG, "dm_validity: bad dtype");
 }

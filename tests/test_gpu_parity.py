@@ -474,3 +474,49 @@ def test_real_geotiff_files_read_once_per_rep(tmp_path, monkeypatch):
     got2 = dm.compute_metrics(src, rec)
     assert got2["max_abs_err"] == orc.compute_metrics(ref, dec2, extras=False)["max_abs_err"]
     assert ingest.STATS["reads"] - r0 == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,nd,with_valid,ref_only", [("int16", -32768, False, False), ("int16", -32768, True, False),
+                                                          ("uint16", 0, False, True), ("uint16", 65535, True, False)])
+def test_nodata_180_bands_vs_oracle(dtype, nd, with_valid, ref_only):
+    """The real EnMAP configuration: 180-band BIP cubes with a nodata value (validity pre-pass through the
+    TMA-staged kernel, masked one-pass kernel with the mask bytes staged next to the tile), all three
+    drop-in results against the oracle.  Whole-pixel nodata, single-band nodata in either cube and
+    band-1-only nodata exercise the three different mask rules."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import quicklooks as ql
+    from oracle import distortion_oracle as orc
+    B, H, W = 180, 45, 67                                   # 3015 pixels: 47 full tiles + a partial one
+    rng = np.random.default_rng(41)
+    ref, dec = _rand_pair(40, dtype, B, H, W, 25)
+    ref[ref == nd] += 1; dec[dec == nd] += 1                # nodata only where planted below
+    whole = rng.random((H, W)) < 0.08
+    ref[:, whole] = nd
+    if not ref_only:
+        dec[:, whole] = nd
+    one = rng.random((H, W)) < 0.03; ref[rng.integers(1, B), one] = nd          # one band of the original
+    if not ref_only:
+        two = rng.random((H, W)) < 0.03; dec[rng.integers(1, B), two] = nd      # one band of the decoded cube
+    b1 = rng.random((H, W)) < 0.02; ref[0, b1] = nd                             # band 1 only (quicklook rule)
+    valid = (rng.random((H, W)) < 0.8) if with_valid else None
+    kw = dict(ref_nodata=nd, tst_nodata=None if ref_only else nd)
+    r_bip = np.ascontiguousarray(np.moveaxis(ref, 0, -1)); d_bip = np.ascontiguousarray(np.moveaxis(dec, 0, -1))
+    got = dm.compute_metrics_arrays(r_bip, d_bip, valid, layout="bip", **kw)
+    _check_metrics(got, orc.compute_metrics(ref, dec, valid, extras=False, **kw))
+    spec = dm.compute_sam_sid_lmse_caseB_arrays(r_bip, d_bip, valid, layout="bip", **kw)
+    for k, w in orc.compute_sam_sid_lmse_caseB(ref, dec, valid, **kw).items():
+        assert _close(spec[k], w), (k, spec[k], w)
+    e = ql.error_max8_arrays(r_bip, d_bip, 255, 32, layout="bip", a_nodata=kw["ref_nodata"], b_nodata=kw["tst_nodata"])
+    o = orc.error_max8(ref, dec, 255, 32, **kw)
+    assert np.array_equal(e["err8_g"], o["err8_g"]) and np.array_equal(e["err8_z"], o["err8_z"])
+    assert np.array_equal(e["valid"], o["valid"])
+    # everything at once through the one-pass kernel (stats + SAM + both planes share the staged mask bytes)
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate
+    from image_compression_analysis_b200.metrics import _valid_to_device
+    import torch
+    pair = DevicePair.from_arrays(r_bip, d_bip, "bip", kw["ref_nodata"], kw["tst_nodata"])
+    P = evaluate(pair, Want(stats=True, sam=True, err8_caps=(255, 32)), _valid_to_device(valid, H, W, "shape"))
+    torch.cuda.synchronize()
+    assert np.array_equal(P.planes["err8_g"].cpu().numpy().reshape(H, W), o["err8_g"])
+    assert np.array_equal(P.planes["err8_z"].cpu().numpy().reshape(H, W), o["err8_z"])
