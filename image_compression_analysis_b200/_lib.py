@@ -9,16 +9,19 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
-DM_BSQ, DM_BIP = 0, 1
+DM_BSQ, DM_BIP, DM_BIL = 0, 1, 2
 DM_VALID_METRICS, DM_VALID_QUICKLOOK, DM_VALID_SPECTRAL = 1, 2, 4
 DM_NSTAT = 8
 DM_S_N, DM_S_X, DM_S_Y, DM_S_XX, DM_S_YY, DM_S_XY, DM_S_ABS, DM_S_SSE = range(8)
 DM_M_MAXERR, DM_M_ABSXY, DM_M_UMAX, DM_M_UNEGMIN, DM_M_LOW4, DM_M_LOW2 = range(6)
 DM_STATS_NO_MOMENTS, DM_STATS_GENERIC = 1, 2
+DM_REQ_TRUNC, DM_REQ_ROUND = 0, 1
+DM_EM_MEAN, DM_EM_RMS, DM_EM_COUNT3, DM_EM_MAX, DM_EM_P95 = range(5)
+DM_DIFF_MODULO, DM_DIFF_SATURATE = 0, 1
 
 LIB_PATH = Path(__file__).resolve().parent / "libdm_b200.so"
 
@@ -31,6 +34,14 @@ class DmPair(C.Structure):
         ("bands", C.c_int64), ("rows", C.c_int64), ("width", C.c_int64), ("band_stride", C.c_int64),
         ("ref_has_nodata", C.c_int32), ("ref_nodata", C.c_int32),
         ("tst_has_nodata", C.c_int32), ("tst_nodata", C.c_int32),
+    ]
+
+
+class DmCube(C.Structure):
+    """dm_cube_t"""
+    _fields_ = [
+        ("data", C.c_void_p), ("dtype", C.c_int32), ("layout", C.c_int32),
+        ("bands", C.c_int64), ("rows", C.c_int64), ("width", C.c_int64), ("band_stride", C.c_int64),
     ]
 
 
@@ -61,6 +72,13 @@ SYMBOLS = {
     "dm_ssim_gauss": (C.c_int, [C.POINTER(DmPair), C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_combine_partials": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_bip_to_bsq": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "dm_band_hist": (C.c_int, [C.POINTER(DmCube), C.POINTER(C.c_int32), C.c_int32, _P, C.c_int32, _P, _P]),
+    "dm_lut_bands_u8": (C.c_int, [C.POINTER(DmCube), C.POINTER(C.c_int32), C.c_int32, _P, _P, _P]),
+    "dm_requantize": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "dm_scene_error": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P]),
+    "dm_scale_plane_u8": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, _P, _P]),
+    "dm_diff1": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "dm_interleave": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
 }
 
 _lib = None

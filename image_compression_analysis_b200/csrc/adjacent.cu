@@ -1,0 +1,639 @@
+// Rows either side of the distortion path: the RGB quicklook, the baseline builders'
+// requantisation and scene error maps, and the codec wrappers' reversible band differencing.  All of it
+// is streaming integer work bounded by HBM; nothing here is staged through the host.
+//
+//   band_hist16        /root/reference/tools/quicklooks.py:51-72    exact 65536-bin value histograms (percentiles)
+//   lut_bands          /root/reference/tools/quicklooks.py:81-89    stretch8 through host-built tables
+//   requantize         /root/reference/tools/make_baseline_B.py:281-316 (k-LSB truncation, nodata kept)
+//                      /root/reference/tools/make_baseline_A.py:166-167 (round to a multiple of 16)
+//   scene_error        /root/reference/tools/make_baseline_B.py:324-419 (modes mean / rms / count3 / max / p95)
+//   diff1              /root/reference/tools/codecs/ccsds121/ccsds121_wrap.py:66-85 (mod 2^16)
+//                      /root/reference/tools/codecs/jpegls/jpegls_wrap.py:92-120   (mod 2^N, int16 saturating)
+
+#include "dm_common.cuh"
+
+namespace dm {
+
+namespace {
+
+// unsigned bin of a sample: int16 in offset binary so that bins are in value order
+template <int DT> __device__ __forceinline__ unsigned bin_of(unsigned raw) {
+  return DT == DM_I16 ? ((raw ^ 0x8000u) & 0xffffu) : raw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact value histogram of selected bands.  One block keeps ALL 65536 bins in shared memory as packed
+// 16-bit counters (128 KB) and flushes them to the int64 global histogram before any counter can
+// overflow (a flush period covers at most 65535 pixels), so the pass reads every selected sample once
+// and global atomics only see the distinct values of a period.
+constexpr int kHistThreads = 1024;
+constexpr int kHistPeriod = 61440;          // pixels per flush period (< 65536, multiple of kHistThreads)
+
+struct HistArgs {
+  const void* data;
+  const uint8_t* plane;
+  int plane_bit;
+  int64_t npix, sb, sp;
+  int sel[4];
+  int64_t* hist;           // nsel x 65536
+};
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(kHistThreads, 1)
+band_hist16_kernel(HistArgs g) {
+  extern __shared__ unsigned packed[];            // 32768 words: bin v -> half (v & 1) of word v >> 1
+  const T* src = static_cast<const T*>(g.data) + (int64_t)g.sel[blockIdx.y] * g.sb;
+  int64_t* out = g.hist + (int64_t)blockIdx.y * 65536;
+  for (int i = threadIdx.x; i < 32768; i += kHistThreads) packed[i] = 0u;
+  __syncthreads();
+  const int64_t nper = (g.npix + kHistPeriod - 1) / kHistPeriod;
+  for (int64_t per = blockIdx.x; per < nper; per += gridDim.x) {
+    const int64_t p0 = per * kHistPeriod;
+    const int64_t p1 = p0 + kHistPeriod < g.npix ? p0 + kHistPeriod : g.npix;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += kHistThreads) {
+      if (g.plane && !(g.plane[p] & g.plane_bit)) continue;
+      const unsigned v = bin_of<DT>((unsigned)(uint16_t)src[p * g.sp]);
+      atomicAdd(&packed[v >> 1], 1u << (16 * (v & 1u)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32768; i += kHistThreads) {
+      const unsigned w = packed[i];
+      if (w) {
+        if (w & 0xffffu) atomic_add_i64(out + 2 * i, (long long)(w & 0xffffu));
+        if (w >> 16) atomic_add_i64(out + 2 * i + 1, (long long)(w >> 16));
+        packed[i] = 0u;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c][p] = lut[c][bin(sample(sel[c], p))]: the reference's float32 stretch is elementwise on an integer
+// sample, so the host tabulates it with the reference's own expression and the planes are bit-exact.
+struct LutArgs {
+  const void* data;
+  int64_t npix, sb, sp;
+  int sel[4];
+  int nsel;
+  const uint8_t* luts;     // nsel x 65536
+  uint8_t* out;            // nsel x npix
+};
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(256)
+lut_bands_kernel(LutArgs g) {
+  const int c = blockIdx.y;
+  const T* src = static_cast<const T*>(g.data) + (int64_t)g.sel[c] * g.sb;
+  const uint8_t* lut = g.luts + (int64_t)c * 65536;
+  uint8_t* out = g.out + (int64_t)c * g.npix;
+  // four pixels per thread: one 32-bit store
+  const int64_t nq = g.npix >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    unsigned w = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned v = bin_of<DT>((unsigned)(uint16_t)src[(4 * q + j) * g.sp]);
+      w |= (unsigned)__ldg(lut + v) << (8 * j);
+    }
+    if ((reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+      reinterpret_cast<unsigned*>(out)[q] = w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[4 * q + j] = (uint8_t)(w >> (8 * j));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (g.npix & 3)) {
+    const int64_t p = 4 * nq + threadIdx.x;
+    out[p] = __ldg(lut + bin_of<DT>((unsigned)(uint16_t)src[p * g.sp]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Requantisation of 16-bit samples, two per 32-bit lane.
+//   mode 0: ((u >> k) << k) on the uint16 view; samples equal to nodata keep their value
+//   mode 1: ((u + 2^(k-1)) >> k) << k in uint16 arithmetic (the sum wraps, as numpy's does)
+__device__ __forceinline__ unsigned requant2(unsigned w, int mode, unsigned keep, unsigned half2, unsigned nd2, bool has_nd) {
+  unsigned r;
+  if (mode == 0) {
+    r = w & keep;
+    if (has_nd) {
+      const unsigned eq = __vcmpeq2(w, nd2);      // 0xffff per equal half
+      r = (r & ~eq) | (w & eq);
+    }
+  } else {
+    r = __vadd2(w, half2) & keep;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+requantize_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t n, int mode, int k,
+                  int has_nd, unsigned nd) {
+  const unsigned keep1 = (0xffffu >> k) << k, keep = keep1 | (keep1 << 16);
+  const unsigned half1 = k > 0 ? (1u << (k - 1)) : 0u, half2 = half1 | (half1 << 16);
+  const unsigned nd2 = (nd & 0xffffu) | (nd << 16);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  int64_t done = 0;
+  if (aligned) {
+    const int64_t nv = n >> 3;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int64_t i = tid; i < nv; i += nth) {
+      uint4 v = ldg_stream16(s4 + i);
+      v.x = requant2(v.x, mode, keep, half2, nd2, has_nd);
+      v.y = requant2(v.y, mode, keep, half2, nd2, has_nd);
+      v.z = requant2(v.z, mode, keep, half2, nd2, has_nd);
+      v.w = requant2(v.w, mode, keep, half2, nd2, has_nd);
+      __stcs(d4 + i, v);
+    }
+    done = nv << 3;
+  }
+  for (int64_t i = done + tid; i < n; i += nth) {
+    const unsigned w = src[i];
+    dst[i] = (uint16_t)requant2(w, mode, keep, half2, nd2, has_nd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scene error maps: per pixel, walk the bands IN ORDER (the reference accumulates float32 planes band by
+// band, make_baseline_B.py:345-361, so the rounding sequence of the rms mode is part of the result).
+enum { EM_MEAN = 0, EM_RMS = 1, EM_COUNT3 = 2, EM_MAX = 3, EM_P95 = 4 };
+
+struct PixelAcc {
+  float acc;                          // mean: sum d   rms: sum d*d   (float32, rounded per band)
+  unsigned cnt, mx;
+  unsigned long long h[4];            // p95: 16 packed 16-bit counters
+  __device__ __forceinline__ void init() { acc = 0.f; cnt = 0; mx = 0; h[0] = h[1] = h[2] = h[3] = 0ull; }
+  template <int MODE> __device__ __forceinline__ void add(int d, int kmax) {
+    if (MODE == EM_MEAN) acc = __double2float_rn((double)acc + (double)d);
+    if (MODE == EM_RMS) acc = __double2float_rn((double)acc + (double)(int)((unsigned)d * (unsigned)d));   // int32 product wraps
+    if (MODE == EM_COUNT3) cnt += d == kmax;
+    if (MODE == EM_MAX) mx = max(mx, (unsigned)d & 0xffffu);
+    if (MODE == EM_P95) {
+      const int k = min(d, kmax);
+      const unsigned long long inc = 1ull << (16 * (k & 3));
+#pragma unroll
+      for (int w = 0; w < 4; ++w) h[w] += (k >> 2) == w ? inc : 0ull;
+    }
+  }
+  template <int MODE> __device__ __forceinline__ float finish(int bands, int kmax, unsigned thr) const {
+    if (MODE == EM_MEAN) return __fdiv_rn(acc, (float)bands);
+    if (MODE == EM_RMS) return __fsqrt_rn(__fdiv_rn(acc, (float)bands));
+    if (MODE == EM_COUNT3) return (float)(cnt & 0xffffu);
+    if (MODE == EM_MAX) return (float)mx;
+    // p95 (make_baseline_B.py:362-368): first bin k with cdf[k] >= thr, assigned only while the output
+    // is still 0 -- so a hit at k = 0 leaves it open for k = 1 (kept as the reference has it)
+    unsigned cdf = 0;
+    float out = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k <= kmax) {
+        cdf += (unsigned)(h[k >> 2] >> (16 * (k & 3))) & 0xffffu;
+        if (cdf >= thr && out == 0.f) out = (float)k;
+      }
+    }
+    return out;
+  }
+};
+
+struct SceneArgs {
+  const void* ref;
+  const void* tst;
+  const uint8_t* valid;      // (rows*width) nonzero = valid, or NULL
+  int64_t bands, npix, sb;
+  int kmax;
+  unsigned thr;
+  float* out;
+  unsigned* out_max;         // bit pattern of the largest (non-negative) output value, atomicMax
+};
+
+__device__ __forceinline__ void block_max_to(unsigned* dst, float v) {
+  // outputs are >= 0 (or NaN in the rms mode when the reference's int32 square wraps), so the bit
+  // patterns order like the values
+  unsigned b = __float_as_uint(v);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+  if ((threadIdx.x & 31) == 0 && b) atomicMax(dst, b);
+}
+
+// BSQ: thread per pixel, every band coalesced across the warp; eight bands of both cubes in flight
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+scene_error_bsq(SceneArgs g) {
+  const T* ref = static_cast<const T*>(g.ref);
+  const T* tst = static_cast<const T*>(g.tst);
+  const int B = (int)g.bands;
+  float vmax = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < g.npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const bool ok = !g.valid || g.valid[p];
+    PixelAcc a;
+    a.init();
+    int b = 0;
+    for (; b + 8 <= B; b += 8) {
+      int x[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { x[j] = (int)__ldg(ref + (b + j) * g.sb + p); y[j] = (int)__ldg(tst + (b + j) * g.sb + p); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a.add<MODE>(ok ? abs(x[j] - y[j]) : 0, g.kmax);
+    }
+    for (; b < B; ++b) {
+      const int x = (int)__ldg(ref + b * g.sb + p), y = (int)__ldg(tst + b * g.sb + p);
+      a.add<MODE>(ok ? abs(x - y) : 0, g.kmax);
+    }
+    const float v = a.finish<MODE>(B, g.kmax, g.thr);
+    g.out[p] = v;
+    vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
+  }
+  block_max_to(g.out_max, vmax);
+}
+
+// BIP: a tile of kTile pixels (both cubes) is copied to shared memory with coalesced 16-byte (or 2-byte)
+// loads, then thread t walks the spectrum of pixel t
+constexpr int kSceneTile = 64;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kSceneTile)
+scene_error_bip(SceneArgs g) {
+  extern __shared__ __align__(16) unsigned char tile[];
+  const int B = (int)g.bands;
+  const int64_t tile_elems = (int64_t)kSceneTile * B;
+  T* sa = reinterpret_cast<T*>(tile);
+  T* sr = sa + tile_elems;
+  const T* ref = static_cast<const T*>(g.ref);
+  const T* tst = static_cast<const T*>(g.tst);
+  const int64_t ntiles = (g.npix + kSceneTile - 1) / kSceneTile;
+  const bool vec = ((reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(tst)) & 15) == 0 &&
+                   (tile_elems * sizeof(T)) % 16 == 0;
+  float vmax = 0.f;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t p0 = t * kSceneTile;
+    const int np = (int)((g.npix - p0) < kSceneTile ? (g.npix - p0) : kSceneTile);
+    const int64_t e0 = p0 * B, ne = (int64_t)np * B;
+    __syncthreads();
+    if (vec && np == kSceneTile) {
+      const int nv = (int)(ne * sizeof(T) / 16);
+      const uint4* ga = reinterpret_cast<const uint4*>(ref + e0);
+      const uint4* gr = reinterpret_cast<const uint4*>(tst + e0);
+      for (int i = threadIdx.x; i < nv; i += kSceneTile) {
+        reinterpret_cast<uint4*>(sa)[i] = ldg_stream16(ga + i);
+        reinterpret_cast<uint4*>(sr)[i] = ldg_stream16(gr + i);
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < ne; i += kSceneTile) { sa[i] = ref[e0 + i]; sr[i] = tst[e0 + i]; }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < np) {
+      const int64_t p = p0 + threadIdx.x;
+      const bool ok = !g.valid || g.valid[p];
+      PixelAcc a;
+      a.init();
+      const T* xa = sa + (int64_t)threadIdx.x * B;
+      const T* xr = sr + (int64_t)threadIdx.x * B;
+      for (int b = 0; b < B; ++b) a.add<MODE>(ok ? abs((int)xa[b] - (int)xr[b]) : 0, g.kmax);
+      const float v = a.finish<MODE>(B, g.kmax, g.thr);
+      g.out[p] = v;
+      vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
+    }
+  }
+  block_max_to(g.out_max, vmax);
+}
+
+// (np.clip(v, 0, emax) * (255.0/emax) + 0.5).astype(np.uint8): a float32 chain (make_baseline_B.py:417)
+__global__ void __launch_bounds__(256)
+scale_plane_u8_kernel(const float* __restrict__ plane, int64_t n, float emax, float scale, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float c = fminf(fmaxf(plane[i], 0.f), emax);
+    out[i] = (uint8_t)(int)__fadd_rn(__fmul_rn(c, scale), 0.5f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Band differencing along the band axis of a BSQ cube.  Thread <-> one 16-byte vector of pixels (or one
+// pixel in the unaligned fallback); the previous band stays in registers, so every sample is read once
+// and written once.
+//   arith 0: modulo 2^N   (uint16 / int16 view / uint8)      forward R[b] = X[b] - X[b-1], inverse running sum
+//   arith 1: int16 saturating (jpegls_wrap.py:100-102, 114-116): R = clip(X[b] - X[b-1]), X[b] = clip(R[b] + X[b-1])
+template <int EB, int ARITH> __device__ __forceinline__ unsigned vsub(unsigned a, unsigned b) {
+  if (ARITH == 1) return __vsubss2(a, b);
+  return EB == 2 ? __vsub2(a, b) : __vsub4(a, b);
+}
+template <int EB, int ARITH> __device__ __forceinline__ unsigned vadd(unsigned a, unsigned b) {
+  if (ARITH == 1) return __vaddss2(a, b);
+  return EB == 2 ? __vadd2(a, b) : __vadd4(a, b);
+}
+
+template <int EB, int ARITH, bool INVERSE>
+__global__ void __launch_bounds__(256)
+diff1_vec_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t bands, int64_t nvec, int64_t sbv) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    uint4 prev = ldg_stream16(src + i);
+    __stcs(dst + i, prev);
+    int64_t b = 1;
+    for (; b + 4 <= bands; b += 4) {
+      uint4 c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = ldg_stream16(src + (b + j) * sbv + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        if (INVERSE) {
+          o.x = vadd<EB, ARITH>(c[j].x, prev.x); o.y = vadd<EB, ARITH>(c[j].y, prev.y);
+          o.z = vadd<EB, ARITH>(c[j].z, prev.z); o.w = vadd<EB, ARITH>(c[j].w, prev.w);
+          prev = o;
+        } else {
+          o.x = vsub<EB, ARITH>(c[j].x, prev.x); o.y = vsub<EB, ARITH>(c[j].y, prev.y);
+          o.z = vsub<EB, ARITH>(c[j].z, prev.z); o.w = vsub<EB, ARITH>(c[j].w, prev.w);
+          prev = c[j];
+        }
+        __stcs(dst + (b + j) * sbv + i, o);
+      }
+    }
+    for (; b < bands; ++b) {
+      const uint4 c = ldg_stream16(src + b * sbv + i);
+      uint4 o;
+      if (INVERSE) {
+        o.x = vadd<EB, ARITH>(c.x, prev.x); o.y = vadd<EB, ARITH>(c.y, prev.y);
+        o.z = vadd<EB, ARITH>(c.z, prev.z); o.w = vadd<EB, ARITH>(c.w, prev.w);
+        prev = o;
+      } else {
+        o.x = vsub<EB, ARITH>(c.x, prev.x); o.y = vsub<EB, ARITH>(c.y, prev.y);
+        o.z = vsub<EB, ARITH>(c.z, prev.z); o.w = vsub<EB, ARITH>(c.w, prev.w);
+        prev = c;
+      }
+      __stcs(dst + b * sbv + i, o);
+    }
+  }
+}
+
+template <typename T, int ARITH, bool INVERSE>
+__global__ void __launch_bounds__(256)
+diff1_scalar_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t bands, int64_t npix, int64_t sb) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    int prev = (int)src[p];
+    dst[p] = (T)prev;
+    for (int64_t b = 1; b < bands; ++b) {
+      const int c = (int)src[b * sb + p];
+      int o = INVERSE ? c + prev : c - prev;
+      if (ARITH == 1) o = max(-32768, min(32767, o));
+      dst[b * sb + p] = (T)o;                       // the cast wraps modulo 2^N
+      prev = INVERSE ? (int)(T)o : c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interleave conversions.  BSQ (B,H,W) <-> BIL (H,B,W) moves whole rows; everything that involves BIP is
+// a batched 2-D transpose [batch][R][C] -> [batch][C][R] through a padded shared-memory tile.
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t Cn, int64_t tiles_c, int64_t batch0) {
+  __shared__ T tile[64][65];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+  const int64_t batch = batch0 + blockIdx.y;
+  const T* s = src + batch * R * Cn;
+  T* d = dst + batch * R * Cn;
+  const int64_t r0 = ((int64_t)blockIdx.x / tiles_c) * 64, c0 = ((int64_t)blockIdx.x % tiles_c) * 64;
+#pragma unroll 4
+  for (int j = 0; j < 64; j += 4) {
+    const int64_t r = r0 + ty + j, c = c0 + tx;
+    if (r < R && c < Cn) tile[ty + j][tx] = s[r * Cn + c];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int j = 0; j < 64; j += 4) {
+    const int64_t c = c0 + ty + j, r = r0 + tx;
+    if (r < R && c < Cn) d[c * R + r] = tile[tx][ty + j];
+  }
+}
+
+// dst row (i1, i0) <- src row (i0, i1), rows of `len` bytes: BSQ <-> BIL
+__global__ void __launch_bounds__(256)
+swap_rows_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int64_t n0, int64_t n1, int64_t len) {
+  const int64_t nrows = n0 * n1;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)len) & 15) == 0;
+  for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int64_t i0 = row / n1, i1 = row % n1;
+    const unsigned char* s = src + row * len;
+    unsigned char* d = dst + (i1 * n0 + i0) * len;
+    if (vec) {
+      for (int64_t i = threadIdx.x; i < (len >> 4); i += blockDim.x)
+        __stcs(reinterpret_cast<uint4*>(d) + i, ldg_stream16(reinterpret_cast<const uint4*>(s) + i));
+    } else {
+      for (int64_t i = threadIdx.x; i < len; i += blockDim.x) d[i] = s[i];
+    }
+  }
+}
+
+int grid_for(int64_t work_items, int threads, int per_sm) {
+  const int sms = sm_count();
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)(sms > 0 ? sms : 148) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int check_cube(const dm_cube_t& c, const char* who) {
+  if (!c.data) return fail(DM_EARG, "%s: null cube", who);
+  if (c.dtype != DM_U8 && c.dtype != DM_U16 && c.dtype != DM_I16) return fail(DM_EARG, "%s: bad dtype", who);
+  if (c.layout != DM_BSQ && c.layout != DM_BIP) return fail(DM_EARG, "%s: layout must be DM_BSQ or DM_BIP", who);
+  if (c.bands <= 0 || c.rows < 0 || c.width < 0) return fail(DM_EARG, "%s: bad geometry", who);
+  if (c.layout == DM_BSQ && c.band_stride < c.rows * c.width) return fail(DM_EARG, "%s: band_stride < rows*width", who);
+  return DM_OK;
+}
+
+}  // namespace
+
+int launch_band_hist(const dm_cube_t& c, const int32_t* sel, int nsel, const uint8_t* plane, int plane_bit,
+                     int64_t* hist, cudaStream_t s) {
+  if (int rc = check_cube(c, "dm_band_hist")) return rc;
+  if (!sel || !hist || nsel < 1 || nsel > 4) return fail(DM_EARG, "dm_band_hist: 1..4 selected bands and a histogram");
+  HistArgs g{};
+  g.data = c.data; g.plane = plane; g.plane_bit = plane_bit; g.npix = c.rows * c.width; g.hist = hist;
+  g.sb = c.layout == DM_BSQ ? c.band_stride : 1;
+  g.sp = c.layout == DM_BSQ ? 1 : c.bands;
+  for (int i = 0; i < nsel; ++i) {
+    if (sel[i] < 0 || sel[i] >= c.bands) return fail(DM_EARG, "dm_band_hist: band index %d out of range", (int)sel[i]);
+    g.sel[i] = sel[i];
+  }
+  if (g.npix == 0) return DM_OK;
+  const int64_t nper = (g.npix + kHistPeriod - 1) / kHistPeriod;
+  const int sms = sm_count();
+  if (sms < 0) return DM_ECUDA;
+  const dim3 grid((unsigned)(nper < sms ? nper : sms), (unsigned)nsel);
+  const size_t smem = 32768 * sizeof(unsigned);
+#define DM_HIST(T, DT)                                                                                         \
+  do {                                                                                                         \
+    DM_CUDA(cudaFuncSetAttribute(band_hist16_kernel<T, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    band_hist16_kernel<T, DT><<<grid, kHistThreads, smem, s>>>(g);                                             \
+  } while (0)
+  if (c.dtype == DM_U8) DM_HIST(uint8_t, DM_U8);
+  else if (c.dtype == DM_U16) DM_HIST(uint16_t, DM_U16);
+  else DM_HIST(uint16_t, DM_I16);
+#undef DM_HIST
+  DM_LAUNCH_CHECK("band_hist16");
+  return DM_OK;
+}
+
+int launch_lut_bands(const dm_cube_t& c, const int32_t* sel, int nsel, const uint8_t* luts, uint8_t* out, cudaStream_t s) {
+  if (int rc = check_cube(c, "dm_lut_bands_u8")) return rc;
+  if (!sel || !luts || !out || nsel < 1 || nsel > 4) return fail(DM_EARG, "dm_lut_bands_u8: 1..4 selected bands, tables and an output");
+  LutArgs g{};
+  g.data = c.data; g.npix = c.rows * c.width; g.nsel = nsel; g.luts = luts; g.out = out;
+  g.sb = c.layout == DM_BSQ ? c.band_stride : 1;
+  g.sp = c.layout == DM_BSQ ? 1 : c.bands;
+  for (int i = 0; i < nsel; ++i) {
+    if (sel[i] < 0 || sel[i] >= c.bands) return fail(DM_EARG, "dm_lut_bands_u8: band index %d out of range", (int)sel[i]);
+    g.sel[i] = sel[i];
+  }
+  if (g.npix == 0) return DM_OK;
+  const dim3 grid((unsigned)grid_for((g.npix + 3) / 4, 256, 8), (unsigned)nsel);
+  if (c.dtype == DM_U8) lut_bands_kernel<uint8_t, DM_U8><<<grid, 256, 0, s>>>(g);
+  else if (c.dtype == DM_U16) lut_bands_kernel<uint16_t, DM_U16><<<grid, 256, 0, s>>>(g);
+  else lut_bands_kernel<uint16_t, DM_I16><<<grid, 256, 0, s>>>(g);
+  DM_LAUNCH_CHECK("lut_bands");
+  return DM_OK;
+}
+
+int launch_requantize(const void* src, void* dst, int dtype, int64_t n, int mode, int k, int has_nodata, int nodata,
+                      cudaStream_t s) {
+  if (!src || !dst) return fail(DM_EARG, "dm_requantize: null pointer");
+  if (dtype != DM_U16 && dtype != DM_I16) return fail(DM_EUNSUPPORTED, "dm_requantize: 16-bit samples only");
+  if (n < 0 || k < 0 || k > 15 || (mode != 0 && mode != 1)) return fail(DM_EARG, "dm_requantize: bad arguments");
+  if (n == 0) return DM_OK;
+  requantize_kernel<<<grid_for((n + 7) / 8, 256, 8), 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst),
+                                                                   n, mode, k, has_nodata && mode == 0, (unsigned)nodata & 0xffffu);
+  DM_LAUNCH_CHECK("requantize");
+  return DM_OK;
+}
+
+template <typename T>
+static int scene_dispatch(const dm_pair_t& p, SceneArgs& g, int mode, cudaStream_t s) {
+  const bool bsq = p.layout == DM_BSQ;
+  const size_t smem = 2 * (size_t)kSceneTile * (size_t)p.bands * sizeof(T);
+  if (!bsq && smem > 200 * 1024) return fail(DM_EUNSUPPORTED, "dm_scene_error: too many bands for the BIP tile");
+  const int sms = sm_count();
+  if (sms < 0) return DM_ECUDA;
+#define DM_SCENE(MODE)                                                                                          \
+  do {                                                                                                          \
+    if (bsq) {                                                                                                  \
+      scene_error_bsq<T, MODE><<<grid_for(g.npix, 256, 8), 256, 0, s>>>(g);                                     \
+    } else {                                                                                                    \
+      DM_CUDA(cudaFuncSetAttribute(scene_error_bip<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      const int64_t fit = (int64_t)(200 * 1024) / (int64_t)smem, ntiles = (g.npix + kSceneTile - 1) / kSceneTile;      \
+      const int64_t cap = (int64_t)sms * (fit < 1 ? 1 : (fit > 16 ? 16 : fit));                                         \
+      scene_error_bip<T, MODE><<<(unsigned)(ntiles < cap ? ntiles : cap), kSceneTile, smem, s>>>(g);                    \
+    }                                                                                                           \
+  } while (0)
+  switch (mode) {
+    case EM_MEAN: DM_SCENE(EM_MEAN); break;
+    case EM_RMS: DM_SCENE(EM_RMS); break;
+    case EM_COUNT3: DM_SCENE(EM_COUNT3); break;
+    case EM_MAX: DM_SCENE(EM_MAX); break;
+    case EM_P95: DM_SCENE(EM_P95); break;
+    default: return fail(DM_EARG, "dm_scene_error: bad mode");
+  }
+#undef DM_SCENE
+  DM_LAUNCH_CHECK("scene_error");
+  return DM_OK;
+}
+
+int launch_scene_error(const dm_pair_t& p, const uint8_t* valid, int mode, int k_bits, uint32_t p95_thr, float* out_plane,
+                       uint32_t* out_max_bits, cudaStream_t s) {
+  if (!p.ref || !p.tst || !out_plane || !out_max_bits) return fail(DM_EARG, "dm_scene_error: null pointer");
+  if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_scene_error: bad layout");
+  if (p.bands <= 0 || p.bands > 65535 || p.rows < 0 || p.width < 0) return fail(DM_EARG, "dm_scene_error: bad geometry");
+  if (k_bits < 0 || k_bits > 16) return fail(DM_EARG, "dm_scene_error: k_bits out of range");
+  if (mode == EM_P95 && k_bits > 4) return fail(DM_EUNSUPPORTED, "dm_scene_error: p95 keeps at most 16 bins per pixel (k_bits <= 4)");
+  SceneArgs g{};
+  g.ref = p.ref; g.tst = p.tst; g.valid = valid; g.bands = p.bands; g.npix = p.rows * p.width;
+  g.sb = p.layout == DM_BSQ ? p.band_stride : 1;
+  g.kmax = (1 << k_bits) - 1; g.thr = p95_thr; g.out = out_plane; g.out_max = out_max_bits;
+  if (g.npix == 0) return DM_OK;
+  switch (p.dtype) {
+    case DM_U8: return scene_dispatch<uint8_t>(p, g, mode, s);
+    case DM_U16: return scene_dispatch<uint16_t>(p, g, mode, s);
+    case DM_I16: return scene_dispatch<int16_t>(p, g, mode, s);
+  }
+  return fail(DM_EARG, "dm_scene_error: bad dtype");
+}
+
+int launch_scale_plane_u8(const float* plane, int64_t n, float emax, float scale, uint8_t* out, cudaStream_t s) {
+  if (!plane || !out) return fail(DM_EARG, "dm_scale_plane_u8: null pointer");
+  if (n <= 0) return DM_OK;
+  scale_plane_u8_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(plane, n, emax, scale, out);
+  DM_LAUNCH_CHECK("scale_plane_u8");
+  return DM_OK;
+}
+
+int launch_diff1(const void* src, void* dst, int dtype, int arith, int inverse, int64_t bands, int64_t npix,
+                 int64_t band_stride, cudaStream_t s) {
+  if (!src || !dst) return fail(DM_EARG, "dm_diff1: null pointer");
+  if (bands <= 0 || npix < 0 || band_stride < npix) return fail(DM_EARG, "dm_diff1: bad geometry");
+  if (arith != 0 && arith != 1) return fail(DM_EARG, "dm_diff1: arith must be 0 (modulo) or 1 (saturating)");
+  if (arith == 1 && dtype != DM_I16) return fail(DM_EARG, "dm_diff1: saturating arithmetic is the int16 variant");
+  if (npix == 0) return DM_OK;
+  const int eb = elem_bytes(dtype);
+  const int per16 = 16 / eb;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 &&
+                   band_stride % per16 == 0 && npix % per16 == 0;
+#define DM_DIFF_VEC(EB, AR, INV)                                                                                  \
+  diff1_vec_kernel<EB, AR, INV><<<grid_for(npix / per16, 256, 8), 256, 0, s>>>(                                   \
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), bands, npix / per16, band_stride / per16)
+#define DM_DIFF_SC(T, AR, INV)                                                                                    \
+  diff1_scalar_kernel<T, AR, INV><<<grid_for(npix, 256, 8), 256, 0, s>>>(static_cast<const T*>(src), static_cast<T*>(dst), \
+                                                                        bands, npix, band_stride)
+  if (vec) {
+    if (eb == 1) { if (inverse) DM_DIFF_VEC(1, 0, true); else DM_DIFF_VEC(1, 0, false); }
+    else if (arith == 0) { if (inverse) DM_DIFF_VEC(2, 0, true); else DM_DIFF_VEC(2, 0, false); }
+    else { if (inverse) DM_DIFF_VEC(2, 1, true); else DM_DIFF_VEC(2, 1, false); }
+  } else {
+    if (eb == 1) { if (inverse) DM_DIFF_SC(uint8_t, 0, true); else DM_DIFF_SC(uint8_t, 0, false); }
+    else if (arith == 0) { if (inverse) DM_DIFF_SC(uint16_t, 0, true); else DM_DIFF_SC(uint16_t, 0, false); }
+    else { if (inverse) DM_DIFF_SC(int16_t, 1, true); else DM_DIFF_SC(int16_t, 1, false); }
+  }
+#undef DM_DIFF_VEC
+#undef DM_DIFF_SC
+  DM_LAUNCH_CHECK("diff1");
+  return DM_OK;
+}
+
+int launch_interleave(const void* src, void* dst, int eb, int from, int to, int64_t bands, int64_t rows, int64_t width,
+                      cudaStream_t s) {
+  if (!src || !dst) return fail(DM_EARG, "dm_interleave: null pointer");
+  if (eb != 1 && eb != 2) return fail(DM_EARG, "dm_interleave: elem_bytes must be 1 or 2");
+  if (from < 0 || from > 2 || to < 0 || to > 2) return fail(DM_EARG, "dm_interleave: layouts are DM_BSQ / DM_BIP / DM_BIL");
+  if (bands <= 0 || rows < 0 || width < 0) return fail(DM_EARG, "dm_interleave: bad geometry");
+  const int64_t n = bands * rows * width;
+  if (n == 0) return DM_OK;
+  if (from == to) {
+    DM_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * eb, cudaMemcpyDeviceToDevice, s));
+    return DM_OK;
+  }
+  if ((from == DM_BSQ && to == DM_BIL) || (from == DM_BIL && to == DM_BSQ)) {
+    const int64_t n0 = from == DM_BSQ ? bands : rows, n1 = from == DM_BSQ ? rows : bands;
+    swap_rows_kernel<<<grid_for(n0 * n1 * 256, 256, 16), 256, 0, s>>>(static_cast<const unsigned char*>(src),
+                                                                     static_cast<unsigned char*>(dst), n0, n1, width * eb);
+    DM_LAUNCH_CHECK("swap_rows");
+    return DM_OK;
+  }
+  // transposes: [batch][R][C] -> [batch][C][R]
+  int64_t batch, R, Cn;
+  if (from == DM_BSQ) { batch = 1; R = bands; Cn = rows * width; }            // -> BIP
+  else if (from == DM_BIL) { batch = rows; R = bands; Cn = width; }           // -> BIP
+  else if (to == DM_BSQ) { batch = 1; R = rows * width; Cn = bands; }         // BIP ->
+  else { batch = rows; R = width; Cn = bands; }                               // BIP -> BIL
+  const int64_t gx = (Cn + 63) / 64, gy = (R + 63) / 64;
+  if (gx * gy > 0x7fffffffll) return fail(DM_EUNSUPPORTED, "dm_interleave: cube too large for one launch");
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const dim3 grid((unsigned)(gx * gy), (unsigned)((batch - b0) < 65535 ? (batch - b0) : 65535));
+    if (eb == 1) transpose_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), R, Cn, gx, b0);
+    else transpose_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), R, Cn, gx, b0);
+    DM_LAUNCH_CHECK("transpose");
+  }
+  return DM_OK;
+}
+
+}  // namespace dm

@@ -67,6 +67,19 @@ int launch_combine_partials(const void* gathered, int world, int64_t records, in
 int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands, int64_t rows,
                       int64_t width, cudaStream_t s);
 
+int launch_band_hist(const dm_cube_t& c, const int32_t* sel, int nsel, const uint8_t* plane, int plane_bit,
+                     int64_t* hist, cudaStream_t s);
+int launch_lut_bands(const dm_cube_t& c, const int32_t* sel, int nsel, const uint8_t* luts, uint8_t* out, cudaStream_t s);
+int launch_requantize(const void* src, void* dst, int dtype, int64_t n, int mode, int k, int has_nodata, int nodata,
+                      cudaStream_t s);
+int launch_scene_error(const dm_pair_t& p, const uint8_t* valid, int mode, int k_bits, uint32_t p95_thr, float* out_plane,
+                       uint32_t* out_max_bits, cudaStream_t s);
+int launch_scale_plane_u8(const float* plane, int64_t n, float emax, float scale, uint8_t* out, cudaStream_t s);
+int launch_diff1(const void* src, void* dst, int dtype, int arith, int inverse, int64_t bands, int64_t npix,
+                 int64_t band_stride, cudaStream_t s);
+int launch_interleave(const void* src, void* dst, int eb, int from, int to, int64_t bands, int64_t rows, int64_t width,
+                      cudaStream_t s);
+
 // ---- device side ------------------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -118,4 +118,41 @@ int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands,
   return launch_bip_to_bsq(src, dst, elem_bytes, bands, rows, width, static_cast<cudaStream_t>(stream));
 }
 
+int dm_band_hist(const dm_cube_t* c, const int32_t* sel_bands, int32_t nsel, const uint8_t* plane, int32_t plane_bit,
+                 int64_t* hist, void* stream) {
+  if (!c) return fail(DM_EARG, "dm_band_hist: null cube");
+  return launch_band_hist(*c, sel_bands, nsel, plane, plane_bit, hist, static_cast<cudaStream_t>(stream));
+}
+
+int dm_lut_bands_u8(const dm_cube_t* c, const int32_t* sel_bands, int32_t nsel, const uint8_t* luts, uint8_t* out,
+                    void* stream) {
+  if (!c) return fail(DM_EARG, "dm_lut_bands_u8: null cube");
+  return launch_lut_bands(*c, sel_bands, nsel, luts, out, static_cast<cudaStream_t>(stream));
+}
+
+int dm_requantize(const void* src, void* dst, int32_t dtype, int64_t n, int32_t mode, int32_t k, int32_t has_nodata,
+                  int32_t nodata, void* stream) {
+  return launch_requantize(src, dst, dtype, n, mode, k, has_nodata, nodata, static_cast<cudaStream_t>(stream));
+}
+
+int dm_scene_error(const dm_pair_t* p, const uint8_t* valid, int32_t mode, int32_t k_bits, uint32_t p95_thr,
+                   float* out_plane, uint32_t* out_max_bits, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_scene_error: null pair");
+  return launch_scene_error(*p, valid, mode, k_bits, p95_thr, out_plane, out_max_bits, static_cast<cudaStream_t>(stream));
+}
+
+int dm_scale_plane_u8(const float* plane, int64_t n, float emax, float scale, uint8_t* out, void* stream) {
+  return launch_scale_plane_u8(plane, n, emax, scale, out, static_cast<cudaStream_t>(stream));
+}
+
+int dm_diff1(const void* src, void* dst, int32_t dtype, int32_t arith, int32_t inverse, int64_t bands, int64_t npix,
+             int64_t band_stride, void* stream) {
+  return launch_diff1(src, dst, dtype, arith, inverse, bands, npix, band_stride, static_cast<cudaStream_t>(stream));
+}
+
+int dm_interleave(const void* src, void* dst, int32_t elem_bytes, int32_t from_layout, int32_t to_layout, int64_t bands,
+                  int64_t rows, int64_t width, void* stream) {
+  return launch_interleave(src, dst, elem_bytes, from_layout, to_layout, bands, rows, width, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -202,3 +202,53 @@ def err8_stats_from_hist(hist256: np.ndarray) -> Dict[str, float]:
     mean = s1 / n
     var = (n * s2 - s1 * s1) / (n * n)
     return {"mean": mean, "std": math.sqrt(var)}
+
+
+# ---- RGB quicklook ------------------------------------------------------------------
+def percentiles_from_hist(hist: np.ndarray, first_value: int, pct) -> Optional[tuple]:
+    """np.percentile(v, pct) of the float32 samples behind a value histogram (quicklooks.py:63), without
+    the samples: hist[k] = number of samples equal to first_value + k.
+
+    numpy's "linear" method needs only n and the two order statistics around (n-1)*q; both come
+    straight from the cumulative histogram.  The arithmetic below is numpy's own for a float32 array
+    and float64 quantiles (np.lib._function_base_impl._quantile/_lerp): the difference of the two
+    neighbours in float32, everything else in float64, and the mirrored form for weights >= 0.5.
+    Returns None for an empty selection."""
+    h = np.asarray(hist, dtype=np.int64)
+    n = int(h.sum())
+    if n == 0:
+        return None
+    cum = np.cumsum(h)
+    q = np.true_divide(np.asanyarray(pct), np.float32(100))          # as np.percentile prepares it
+    out = []
+    for qi in np.atleast_1d(q):
+        vi = (n - 1) * qi
+        if vi >= n - 1:
+            ip = inn = n - 1
+        elif vi < 0:
+            ip = inn = 0
+        else:
+            ip = int(np.floor(vi))
+            inn = ip + 1
+        a = np.float32(first_value + int(np.searchsorted(cum, ip, side="right")))
+        b = np.float32(first_value + int(np.searchsorted(cum, inn, side="right")))
+        prev = np.floor(vi) if 0 <= vi < n - 1 else (np.float64(-1) if vi >= n - 1 else np.float64(0))
+        t = np.float64(vi - prev)
+        diff = np.subtract(b, a)                                      # float32
+        r = np.float64(a) + np.float64(diff) * t
+        if t >= 0.5:
+            r = np.float64(b) - np.float64(diff) * (1 - t)
+        out.append(float(r))
+    return tuple(out)
+
+
+def stretch8_lut(lo: float, hi: float, np_dtype) -> np.ndarray:
+    """stretch8 of write_rgb_8bit (quicklooks.py:81-83) tabulated over every value of the sample type,
+    in bin order (int16: -32768 first) -- the expression is the reference's own, on a float32 array."""
+    info = np.iinfo(np.dtype(np_dtype))
+    x = np.arange(info.min, info.max + 1, dtype=np.int64).astype(np.dtype(np_dtype))
+    y = np.clip((x.astype(np.float32) - lo) / (hi - lo + 1e-9), 0, 1)
+    lut = (y * 255.0).astype(np.uint8)
+    if lut.size < 65536:
+        lut = np.concatenate([lut, np.zeros(65536 - lut.size, np.uint8)])
+    return lut

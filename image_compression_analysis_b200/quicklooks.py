@@ -2,8 +2,8 @@
 `--quicklooks <path>`, run_codec.py:419-430): same function names, arguments, file names, tags.
 
   write_error_max8               quicklooks.py:115-207   B200 kernels (dm_spectral)
-  stretch_params_from_baseline   quicklooks.py:51-72     host numpy (off the hot path)
-  write_rgb_8bit                 quicklooks.py:78-109    host numpy (off the hot path)
+  stretch_params_from_baseline   quicklooks.py:51-72     dm_band_hist (exact value histograms) -> percentiles on the host
+  write_rgb_8bit                 quicklooks.py:78-109    dm_lut_bands_u8 (stretch tabulated with the reference's expression)
 
 The error map is max over bands of |A-B| per pixel, zero where either input is invalid, scaled to
 8 bit with the reference's float32 expression.  That expression is elementwise on an integer-valued
@@ -38,49 +38,105 @@ def _valid_mask_from_ds(ds):
     return m
 
 
+def _quicklook_plane(cube_t, np_dtype, layout, B, H, W, nodata):
+    """Device plane with DM_VALID_QUICKLOOK = dataset mask AND band 1 != nodata (quicklooks.py:35-45), or None
+    when the file has no nodata value (everything valid)."""
+    import ctypes as C
+    import torch
+    from . import engine
+    from ._lib import check, lib
+    nd = engine.integral_nodata(nodata, np_dtype)
+    if nd is None:
+        return None
+    # dm_validity works on pairs: the cube stands on both sides, which leaves every bit unchanged
+    pair = DevicePair(cube_t, cube_t, np_dtype, layout, B, H, W, nd, nd)
+    plane = torch.empty(H * W, dtype=torch.uint8, device=cube_t.device)
+    cnt = torch.zeros(3, dtype=torch.int64, device=cube_t.device)
+    cp = pair.c_pair()
+    check(lib().dm_validity(C.byref(cp), None, engine._ptr(plane), engine._ptr(cnt), engine._stream_ptr()))
+    return plane
+
+
+def stretch_params_cube(cube_t, np_dtype, layout, B, H, W, nodata=None, extra_mask=None, rgb_order=RGB_ORDER, pct=(2, 98)):
+    """stretch_params_from_baseline for a device-resident cube: exact value histograms of the three bands
+    (dm_band_hist) -> numpy's interpolated percentiles on the host (finish.percentiles_from_hist)."""
+    import torch
+    from . import adjacent
+    plane = _quicklook_plane(cube_t, np_dtype, layout, B, H, W, nodata)
+    bit = engine_bits()
+    if extra_mask is not None:              # explicit alpha / .msk mask: fold it into the plane
+        m = to_device(np.asarray(extra_mask) > 0).reshape(-1)
+        plane = (m * bit) if plane is None else (plane & (m * bit))
+        plane = plane.to(torch.uint8)
+    sel = [int(i) - 1 for i in rgb_order]
+    hist = adjacent.band_hist(cube_t, np_dtype, layout, B, H, W, sel, plane, bit).cpu().numpy()
+    params = []
+    for h in hist:
+        got = finish.percentiles_from_hist(h, adjacent.first_value(np_dtype), pct)
+        if got is None:
+            lo, hi = 0.0, 1.0
+        else:
+            lo, hi = got
+            if not np.isfinite(lo):
+                lo = 0.0
+            if (not np.isfinite(hi)) or hi <= lo:
+                hi = lo + 1.0
+        params.append((float(lo), float(hi)))
+    return params
+
+
+def engine_bits() -> int:
+    from ._lib import DM_VALID_QUICKLOOK
+    return DM_VALID_QUICKLOOK
+
+
+def rgb_8bit_cube(cube_t, np_dtype, layout, B, H, W, params, rgb_order=RGB_ORDER):
+    """write_rgb_8bit's pixels for a device-resident cube: (3,H,W) uint8 device tensor (dm_lut_bands_u8)."""
+    from . import adjacent
+    luts = np.stack([finish.stretch8_lut(lo, hi, np_dtype) for lo, hi in params], 0)
+    return adjacent.lut_bands_u8(cube_t, np_dtype, layout, B, H, W, [int(i) - 1 for i in rgb_order], luts)
+
+
+def stretch_params_arrays(cube, nodata=None, rgb_order=RGB_ORDER, pct=(2, 98), layout: str = "bsq"):
+    """stretch_params_from_baseline on an in-memory cube ((B,H,W) for "bsq", (H,W,B) for "bip")."""
+    cube = np.asarray(cube)
+    B, H, W = cube.shape if layout == "bsq" else (cube.shape[2], cube.shape[0], cube.shape[1])
+    return stretch_params_cube(to_device(cube), cube.dtype.name, layout, B, H, W, nodata, None, rgb_order, pct)
+
+
+def rgb_8bit_arrays(cube, params, rgb_order=RGB_ORDER, layout: str = "bsq") -> np.ndarray:
+    cube = np.asarray(cube)
+    B, H, W = cube.shape if layout == "bsq" else (cube.shape[2], cube.shape[0], cube.shape[1])
+    return rgb_8bit_cube(to_device(cube), cube.dtype.name, layout, B, H, W, params, rgb_order).cpu().numpy()
+
+
 def stretch_params_from_baseline(path, rgb_order=RGB_ORDER, pct=(2, 98)):
     """Per-channel (lo, hi) percentile stretch ignoring invalid pixels (quicklooks.py:51-72)."""
-    with open_raster(path) as ds:
-        bands = ds.read(rgb_order).astype(np.float32)
-        ok = _valid_mask_from_ds(ds)
-        params = []
-        for ch in bands:
-            v = ch[ok & np.isfinite(ch)]
-            if v.size == 0:
-                lo, hi = 0.0, 1.0
-            else:
-                lo, hi = np.percentile(v, pct)
-                if not np.isfinite(lo):
-                    lo = 0.0
-                if (not np.isfinite(hi)) or hi <= lo:
-                    hi = lo + 1.0
-            params.append((float(lo), float(hi)))
-    return params
+    from .ingest import load_cube
+    c = load_cube(path)
+    return stretch_params_cube(c.tensor, c.np_dtype, c.layout, c.bands, c.rows, c.width, c.nodata, c.mask, rgb_order, pct)
 
 
 def write_rgb_8bit(src_path, out_path, params, rgb_order=RGB_ORDER):
     """8-bit RGB quicklook with the source's valid mask, no nodata carried over (quicklooks.py:78-109)."""
+    from .ingest import load_cube
+    c = load_cube(src_path)
+    assert c.bands >= 3, f"Need ≥3 bands for RGB in {src_path}"
+    rgb = rgb_8bit_cube(c.tensor, c.np_dtype, c.layout, c.bands, c.rows, c.width, params, rgb_order).cpu().numpy()
+    meta = dict(c.meta)
+    meta.update(driver="GTiff", dtype=uint8_dtype(), count=3, photometric="RGB", tiled=True,
+                blockxsize=512, blockysize=512, compress="DEFLATE")
+    meta.pop("nodata", None)
+    out_path = Path(out_path)
+    out_path.parent.mkdir(parents=True, exist_ok=True)
     with open_raster(src_path) as ds:
-        assert ds.count >= 3, f"Need ≥3 bands for RGB in {src_path}"
-        b = ds.read(rgb_order)
-        chans = []
-        for i in range(3):
-            lo, hi = params[i]
-            y = np.clip((b[i].astype(np.float32) - lo) / (hi - lo + 1e-9), 0, 1)
-            chans.append((y * 255.0).astype(np.uint8))
-        rgb = np.stack(chans, 0)
-        meta = ds.meta.copy()
-        meta.update(driver="GTiff", dtype=uint8_dtype(), count=3, photometric="RGB", tiled=True,
-                    blockxsize=512, blockysize=512, compress="DEFLATE")
-        meta.pop("nodata", None)
-        out_path = Path(out_path)
-        out_path.parent.mkdir(parents=True, exist_ok=True)
-        with open_raster(out_path.as_posix(), "w", **meta) as dst:
-            dst.write(rgb)
-            try:
-                dst.write_mask(ds.dataset_mask())
-            except Exception:
-                pass
+        mask = ds.dataset_mask()
+    with open_raster(out_path.as_posix(), "w", **meta) as dst:
+        dst.write(rgb)
+        try:
+            dst.write_mask(mask)
+        except Exception:
+            pass
 
 
 def error_max8_arrays(A, B, err_max_global=255, err_max_zoom=None, pct=(2, 98), *, a_nodata=None, b_nodata=None,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 3
+#define DM_ABI_VERSION 4
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -39,8 +39,8 @@ enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
 /* sample types (the reference path sees uint8 / uint16 / int16: run_codec.py:89-113) */
 enum { DM_U8 = 0, DM_U16 = 1, DM_I16 = 2 };
 
-/* in-memory interleave */
-enum { DM_BSQ = 0, DM_BIP = 1 };
+/* in-memory interleave (DM_BIL, (rows, bands, width), only appears in dm_interleave) */
+enum { DM_BSQ = 0, DM_BIP = 1, DM_BIL = 2 };
 
 /* bits of the per-pixel validity plane written by dm_validity() */
 enum {
@@ -197,6 +197,73 @@ int dm_combine_partials(const void* gathered, int32_t world, int64_t records, in
 /* layout helper: (rows,width,bands) -> (bands,rows,width), same dtype (1 or 2 bytes/sample) */
 int dm_bip_to_bsq(const void* src, void* dst, int32_t elem_bytes, int64_t bands, int64_t rows,
                   int64_t width, void* stream);
+
+
+/* ===== rows either side of the path ========================================= */
+
+/* one cube (same geometry fields as dm_pair_t) */
+typedef struct dm_cube {
+  const void* data;     /* device */
+  int32_t dtype;        /* DM_U8 / DM_U16 / DM_I16 */
+  int32_t layout;       /* DM_BSQ / DM_BIP */
+  int64_t bands, rows, width;
+  int64_t band_stride;  /* DM_BSQ: elements between bands; ignored for DM_BIP */
+} dm_cube_t;
+
+/* RGB quicklook, part 1 -- replaces the sort behind np.percentile in stretch_params_from_baseline
+ * (quicklooks.py:51-72): exact value histograms of up to 4 selected bands (0-based indices in the HOST
+ * array sel_bands), hist[i*65536 + bin] ACCUMULATED, bin = the sample (int16: sample + 32768, so bins
+ * are in value order).  `plane`/`plane_bit` as in dm_fused_stats (NULL = all pixels).  The host turns the
+ * histogram into numpy's linearly interpolated percentiles (finish.percentiles_from_hist). */
+int dm_band_hist(const dm_cube_t* c, const int32_t* sel_bands, int32_t nsel, const uint8_t* plane,
+                 int32_t plane_bit, int64_t* hist, void* stream);
+
+/* RGB quicklook, part 2 -- replaces stretch8 in write_rgb_8bit (quicklooks.py:81-89):
+ * out[i*rows*width + p] = luts[i*65536 + bin(sample(sel_bands[i], p))].  The float32 stretch is an
+ * elementwise function of an integer sample, so the host tabulates it with the reference's own
+ * expression (finish.stretch8_lut) and the planes are bit-exact by construction. */
+int dm_lut_bands_u8(const dm_cube_t* c, const int32_t* sel_bands, int32_t nsel, const uint8_t* luts,
+                    uint8_t* out, void* stream);
+
+/* Baseline builders' requantisation of n 16-bit samples (src may equal dst):
+ *   mode DM_REQ_TRUNC  ((u >> k) << k) on the uint16 view, samples equal to `nodata` untouched
+ *                      (trunc_uint16 / write_truncated_copy, make_baseline_B.py:281-316; "14-in-16" is k = 2)
+ *   mode DM_REQ_ROUND  ((u + 2^(k-1)) >> k) << k in uint16 arithmetic (to_12in16, make_baseline_A.py:166-167, k = 4) */
+enum { DM_REQ_TRUNC = 0, DM_REQ_ROUND = 1 };
+int dm_requantize(const void* src, void* dst, int32_t dtype, int64_t n, int32_t mode, int32_t k,
+                  int32_t has_nodata, int32_t nodata, void* stream);
+
+/* Scene error maps of make_scene_error_map (make_baseline_B.py:324-419): per pixel over the bands IN ORDER,
+ * d = |ref - cmp| (0 where `valid`, uint8 rows*width nonzero = valid, is clear):
+ *   DM_EM_MEAN   float32 sum of d / bands            DM_EM_RMS   sqrt(float32 sum of int32(d*d) / bands)
+ *   DM_EM_COUNT3 #{d == 2^k_bits - 1}                DM_EM_MAX   max d
+ *   DM_EM_P95    the reference's per-pixel histogram percentile (bins 0..2^k_bits-1, k_bits <= 4,
+ *                p95_thr = uint32(bands * 0.95) computed by the host)
+ * out_plane: float32 rows*width (written); out_max_bits: bit pattern of the largest output value
+ * (uint32, atomicMax into a caller-zeroed word; outputs are non-negative).
+ * dm_scale_plane_u8 is the final (clip(v, 0, emax) * scale + 0.5) -> uint8 of make_baseline_B.py:417 with
+ * scale = float32(255.0 / emax) from the host. */
+enum { DM_EM_MEAN = 0, DM_EM_RMS = 1, DM_EM_COUNT3 = 2, DM_EM_MAX = 3, DM_EM_P95 = 4 };
+int dm_scene_error(const dm_pair_t* p, const uint8_t* valid, int32_t mode, int32_t k_bits, uint32_t p95_thr,
+                   float* out_plane, uint32_t* out_max_bits, void* stream);
+int dm_scale_plane_u8(const float* plane, int64_t n, float emax, float scale, uint8_t* out, void* stream);
+
+/* Reversible spectral differencing of the CCSDS-121 / JPEG-LS wrappers along the band axis of a BSQ cube
+ * (bands x npix, `band_stride` elements between bands; src may equal dst):
+ *   arith DM_DIFF_MODULO    R[b] = X[b] - X[b-1] mod 2^N, inverse = running sum mod 2^N
+ *                           (_diff1_bsq_signed/_unsigned, _int1_bsq_*: ccsds121_wrap.py:66-85;
+ *                            _diff1_forward/_inverse uint16, uint8: jpegls_wrap.py:96-99, 110-113, 103-105, 117-119)
+ *   arith DM_DIFF_SATURATE  int16 only: R = clip(X[b] - X[b-1]), X[b] = clip(R[b] + X[b-1]) (jpegls_wrap.py:100-102, 114-116)
+ * inverse = 0 forward, 1 inverse. */
+enum { DM_DIFF_MODULO = 0, DM_DIFF_SATURATE = 1 };
+int dm_diff1(const void* src, void* dst, int32_t dtype, int32_t arith, int32_t inverse, int64_t bands,
+             int64_t npix, int64_t band_stride, void* stream);
+
+/* Raw interleave conversion of the wrappers (_write_raw_interleaved / _read_raw_interleaved,
+ * ccsds121_wrap.py:44-64, ccsds123_wrap.py:43-63): any of DM_BSQ / DM_BIL / DM_BIP to any other,
+ * contiguous cubes of 1- or 2-byte samples. */
+int dm_interleave(const void* src, void* dst, int32_t elem_bytes, int32_t from_layout, int32_t to_layout,
+                  int64_t bands, int64_t rows, int64_t width, void* stream);
 
 #ifdef __cplusplus
 }

@@ -118,9 +118,25 @@ class _Reader:
         }
         return m
 
+    @property
+    def nodatavals(self):
+        return tuple(self._r.nodata for _ in range(self.count))
+
+    @property
+    def profile(self):
+        m = self.meta
+        m.update(tiled=False)
+        return m
+
+    @property
+    def block_shapes(self):
+        return [(min(512, self.height), min(512, self.width)) for _ in range(self.count)]
+
     # pixel access --------------------------------------------------------
-    def read(self, indexes=None, out_dtype=None):
+    def read(self, indexes=None, out_dtype=None, window=None):
         d = self._r.data
+        if window is not None:
+            d = d[:, window.row_off:window.row_off + window.height, window.col_off:window.col_off + window.width]
         if indexes is None:
             out = d.copy()
         elif isinstance(indexes, (list, tuple)):
@@ -162,11 +178,24 @@ class _Writer:
         _REGISTRY[self._key] = r
         return False
 
-    def write(self, arr, indexes=None):
+    def write(self, arr, indexes=None, window=None):
         arr = np.asarray(arr)
-        if arr.ndim == 2:
-            arr = arr[None]
-        self._data = arr.copy()
+        if window is None and indexes is None:
+            if arr.ndim == 2:
+                arr = arr[None]
+            self._data = arr.copy()
+            return
+        # band-wise / windowed writes (the baseline builders): fill a full-size array piece by piece
+        if self._data is None:
+            self._data = np.zeros((self._meta.get("count", 1), self._meta["height"], self._meta["width"]),
+                                  self._meta.get("dtype", arr.dtype))
+        r0, c0 = (window.row_off, window.col_off) if window is not None else (0, 0)
+        if indexes is None:
+            if arr.ndim == 2:
+                arr = arr[None]
+            self._data[:, r0:r0 + arr.shape[1], c0:c0 + arr.shape[2]] = arr
+        else:
+            self._data[int(indexes) - 1, r0:r0 + arr.shape[0], c0:c0 + arr.shape[1]] = arr
 
     def write_mask(self, m):
         self._mask = np.asarray(m) > 0
@@ -184,6 +213,13 @@ def _open(path, mode="r", **meta):
     return _Reader(k, _REGISTRY[k], writable=(mode == "r+"))
 
 
+class Window:
+    """rasterio.windows.Window(col_off, row_off, width, height)"""
+
+    def __init__(self, col_off=0, row_off=0, width=0, height=0):
+        self.col_off, self.row_off, self.width, self.height = int(col_off), int(row_off), int(width), int(height)
+
+
 def install() -> types.ModuleType:
     """Register the stub as `rasterio` in sys.modules (idempotent)."""
     mod = sys.modules.get("rasterio")
@@ -197,4 +233,20 @@ def install() -> types.ModuleType:
     mod.int16 = "int16"
     mod.DatasetReader = _Reader
     sys.modules["rasterio"] = mod
+    # submodules the baseline builders and codec wrappers import at module top
+    win = types.ModuleType("rasterio.windows")
+    win.Window = Window
+    enums = types.ModuleType("rasterio.enums")
+    enums.Resampling = types.SimpleNamespace(nearest=0, bilinear=1, average=5)
+    mod.windows, mod.enums = win, enums
+    sys.modules["rasterio.windows"] = win
+    sys.modules["rasterio.enums"] = enums
+    if "matplotlib" not in sys.modules:           # make_baseline_B.py:34 imports pyplot for plots we never draw
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            mpl = types.ModuleType("matplotlib")
+            mpl.pyplot = types.ModuleType("matplotlib.pyplot")
+            sys.modules["matplotlib"] = mpl
+            sys.modules["matplotlib.pyplot"] = mpl.pyplot
     return mod
