@@ -161,11 +161,16 @@ requantize_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, 
 // band, make_baseline_B.py:345-361, so the rounding sequence of the rms mode is part of the result).
 enum { EM_MEAN = 0, EM_RMS = 1, EM_COUNT3 = 2, EM_MAX = 3, EM_P95 = 4 };
 
+template <int NW>                     // NW 64-bit words of packed 16-bit counters: 4 * NW histogram bins (p95)
 struct PixelAcc {
   float acc;                          // mean: sum d   rms: sum d*d   (float32, rounded per band)
   unsigned cnt, mx;
-  unsigned long long h[4];            // p95: 16 packed 16-bit counters
-  __device__ __forceinline__ void init() { acc = 0.f; cnt = 0; mx = 0; h[0] = h[1] = h[2] = h[3] = 0ull; }
+  unsigned long long h[NW];
+  __device__ __forceinline__ void init() {
+    acc = 0.f; cnt = 0; mx = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) h[w] = 0ull;
+  }
   template <int MODE> __device__ __forceinline__ void add(int d, int kmax) {
     if (MODE == EM_MEAN) acc = __double2float_rn((double)acc + (double)d);
     if (MODE == EM_RMS) acc = __double2float_rn((double)acc + (double)(int)((unsigned)d * (unsigned)d));   // int32 product wraps
@@ -174,8 +179,11 @@ struct PixelAcc {
     if (MODE == EM_P95) {
       const int k = min(d, kmax);
       const unsigned long long inc = 1ull << (16 * (k & 3));
+      if (NW == 1) h[0] += inc;
+      else {
 #pragma unroll
-      for (int w = 0; w < 4; ++w) h[w] += (k >> 2) == w ? inc : 0ull;
+        for (int w = 0; w < NW; ++w) h[w] += (k >> 2) == w ? inc : 0ull;
+      }
     }
   }
   template <int MODE> __device__ __forceinline__ float finish(int bands, int kmax, unsigned thr) const {
@@ -188,7 +196,7 @@ struct PixelAcc {
     unsigned cdf = 0;
     float out = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 4 * NW; ++k) {
       if (k <= kmax) {
         cdf += (unsigned)(h[k >> 2] >> (16 * (k & 3))) & 0xffffu;
         if (cdf >= thr && out == 0.f) out = (float)k;
@@ -218,33 +226,71 @@ __device__ __forceinline__ void block_max_to(unsigned* dst, float v) {
   if ((threadIdx.x & 31) == 0 && b) atomicMax(dst, b);
 }
 
-// BSQ: thread per pixel, every band coalesced across the warp; eight bands of both cubes in flight
-template <typename T, int MODE>
+// BSQ: thread per pixel (VEC2: per pixel PAIR, one 32-bit load per band and cube), every band coalesced
+// across the warp; eight bands of both cubes in flight
+template <typename T, int MODE, int NW, bool VEC2>
 __global__ void __launch_bounds__(256)
 scene_error_bsq(SceneArgs g) {
   const T* ref = static_cast<const T*>(g.ref);
   const T* tst = static_cast<const T*>(g.tst);
   const int B = (int)g.bands;
   float vmax = 0.f;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < g.npix; p += (int64_t)gridDim.x * blockDim.x) {
-    const bool ok = !g.valid || g.valid[p];
-    PixelAcc a;
-    a.init();
-    int b = 0;
-    for (; b + 8 <= B; b += 8) {
-      int x[8], y[8];
+  if (VEC2) {
+    const int64_t npair = g.npix >> 1;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < npair; q += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t p = 2 * q;
+      const bool ok0 = !g.valid || g.valid[p], ok1 = !g.valid || g.valid[p + 1];
+      PixelAcc<NW> a0, a1;
+      a0.init(); a1.init();
+      int b = 0;
+      for (; b + 8 <= B; b += 8) {
+        uint32_t x[8], y[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { x[j] = (int)__ldg(ref + (b + j) * g.sb + p); y[j] = (int)__ldg(tst + (b + j) * g.sb + p); }
+        for (int j = 0; j < 8; ++j) {
+          x[j] = ldg_stream4(ref + (b + j) * g.sb + p);
+          y[j] = ldg_stream4(tst + (b + j) * g.sb + p);
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a.add<MODE>(ok ? abs(x[j] - y[j]) : 0, g.kmax);
+        for (int j = 0; j < 8; ++j) {
+          const int d0 = abs(sample16<sizeof(T) == 2 && T(-1) < T(0) ? DM_I16 : DM_U16>(x[j], 0) -
+                             sample16<sizeof(T) == 2 && T(-1) < T(0) ? DM_I16 : DM_U16>(y[j], 0));
+          const int d1 = abs(sample16<sizeof(T) == 2 && T(-1) < T(0) ? DM_I16 : DM_U16>(x[j], 1) -
+                             sample16<sizeof(T) == 2 && T(-1) < T(0) ? DM_I16 : DM_U16>(y[j], 1));
+          a0.template add<MODE>(ok0 ? d0 : 0, g.kmax);
+          a1.template add<MODE>(ok1 ? d1 : 0, g.kmax);
+        }
+      }
+      for (; b < B; ++b) {
+        const int x0 = (int)__ldg(ref + b * g.sb + p), y0 = (int)__ldg(tst + b * g.sb + p);
+        const int x1 = (int)__ldg(ref + b * g.sb + p + 1), y1 = (int)__ldg(tst + b * g.sb + p + 1);
+        a0.template add<MODE>(ok0 ? abs(x0 - y0) : 0, g.kmax);
+        a1.template add<MODE>(ok1 ? abs(x1 - y1) : 0, g.kmax);
+      }
+      const float v0 = a0.template finish<MODE>(B, g.kmax, g.thr), v1 = a1.template finish<MODE>(B, g.kmax, g.thr);
+      *reinterpret_cast<float2*>(g.out + p) = make_float2(v0, v1);
+      vmax = __uint_as_float(max(__float_as_uint(vmax), max(__float_as_uint(v0), __float_as_uint(v1))));
     }
-    for (; b < B; ++b) {
-      const int x = (int)__ldg(ref + b * g.sb + p), y = (int)__ldg(tst + b * g.sb + p);
-      a.add<MODE>(ok ? abs(x - y) : 0, g.kmax);
+  } else {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < g.npix; p += (int64_t)gridDim.x * blockDim.x) {
+      const bool ok = !g.valid || g.valid[p];
+      PixelAcc<NW> a;
+      a.init();
+      int b = 0;
+      for (; b + 8 <= B; b += 8) {
+        int x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = (int)__ldg(ref + (b + j) * g.sb + p); y[j] = (int)__ldg(tst + (b + j) * g.sb + p); }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.template add<MODE>(ok ? abs(x[j] - y[j]) : 0, g.kmax);
+      }
+      for (; b < B; ++b) {
+        const int x = (int)__ldg(ref + b * g.sb + p), y = (int)__ldg(tst + b * g.sb + p);
+        a.template add<MODE>(ok ? abs(x - y) : 0, g.kmax);
+      }
+      const float v = a.template finish<MODE>(B, g.kmax, g.thr);
+      g.out[p] = v;
+      vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
     }
-    const float v = a.finish<MODE>(B, g.kmax, g.thr);
-    g.out[p] = v;
-    vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
   }
   block_max_to(g.out_max, vmax);
 }
@@ -253,7 +299,7 @@ scene_error_bsq(SceneArgs g) {
 // loads, then thread t walks the spectrum of pixel t
 constexpr int kSceneTile = 64;
 
-template <typename T, int MODE>
+template <typename T, int MODE, int NW>
 __global__ void __launch_bounds__(kSceneTile)
 scene_error_bip(SceneArgs g) {
   extern __shared__ __align__(16) unsigned char tile[];
@@ -287,12 +333,12 @@ scene_error_bip(SceneArgs g) {
     if ((int)threadIdx.x < np) {
       const int64_t p = p0 + threadIdx.x;
       const bool ok = !g.valid || g.valid[p];
-      PixelAcc a;
+      PixelAcc<NW> a;
       a.init();
       const T* xa = sa + (int64_t)threadIdx.x * B;
       const T* xr = sr + (int64_t)threadIdx.x * B;
-      for (int b = 0; b < B; ++b) a.add<MODE>(ok ? abs((int)xa[b] - (int)xr[b]) : 0, g.kmax);
-      const float v = a.finish<MODE>(B, g.kmax, g.thr);
+      for (int b = 0; b < B; ++b) a.template add<MODE>(ok ? abs((int)xa[b] - (int)xr[b]) : 0, g.kmax);
+      const float v = a.template finish<MODE>(B, g.kmax, g.thr);
       g.out[p] = v;
       vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
     }
@@ -516,16 +562,27 @@ static int scene_dispatch(const dm_pair_t& p, SceneArgs& g, int mode, cudaStream
   if (!bsq && smem > 200 * 1024) return fail(DM_EUNSUPPORTED, "dm_scene_error: too many bands for the BIP tile");
   const int sms = sm_count();
   if (sms < 0) return DM_ECUDA;
-#define DM_SCENE(MODE)                                                                                          \
+  // two pixels per thread through 32-bit loads when the geometry allows it (16-bit samples, even strides)
+  const bool vec2 = bsq && sizeof(T) == 2 && g.npix % 2 == 0 && g.sb % 2 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(g.ref) | reinterpret_cast<uintptr_t>(g.tst)) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(g.out) & 7) == 0;
+  const bool small_hist = g.kmax <= 3;          // p95 with k_bits <= 2 (the reference's k): one counter word
+#define DM_SCENE_K(MODE, NW)                                                                                    \
   do {                                                                                                          \
     if (bsq) {                                                                                                  \
-      scene_error_bsq<T, MODE><<<grid_for(g.npix, 256, 8), 256, 0, s>>>(g);                                     \
+      if (vec2) scene_error_bsq<T, MODE, NW, sizeof(T) == 2><<<grid_for(g.npix / 2, 256, 8), 256, 0, s>>>(g);   \
+      else scene_error_bsq<T, MODE, NW, false><<<grid_for(g.npix, 256, 8), 256, 0, s>>>(g);                     \
     } else {                                                                                                    \
-      DM_CUDA(cudaFuncSetAttribute(scene_error_bip<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      DM_CUDA(cudaFuncSetAttribute(scene_error_bip<T, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       const int64_t fit = (int64_t)(200 * 1024) / (int64_t)smem, ntiles = (g.npix + kSceneTile - 1) / kSceneTile;      \
       const int64_t cap = (int64_t)sms * (fit < 1 ? 1 : (fit > 16 ? 16 : fit));                                         \
-      scene_error_bip<T, MODE><<<(unsigned)(ntiles < cap ? ntiles : cap), kSceneTile, smem, s>>>(g);                    \
+      scene_error_bip<T, MODE, NW><<<(unsigned)(ntiles < cap ? ntiles : cap), kSceneTile, smem, s>>>(g);                \
     }                                                                                                           \
+  } while (0)
+#define DM_SCENE(MODE)                                                                                          \
+  do {                                                                                                          \
+    if (MODE == EM_P95 && !small_hist) DM_SCENE_K(MODE, 4);                                                     \
+    else DM_SCENE_K(MODE, 1);                                                                                   \
   } while (0)
   switch (mode) {
     case EM_MEAN: DM_SCENE(EM_MEAN); break;
@@ -536,6 +593,7 @@ static int scene_dispatch(const dm_pair_t& p, SceneArgs& g, int mode, cudaStream
     default: return fail(DM_EARG, "dm_scene_error: bad mode");
   }
 #undef DM_SCENE
+#undef DM_SCENE_K
   DM_LAUNCH_CHECK("scene_error");
   return DM_OK;
 }
