@@ -2,12 +2,15 @@
 //
 // Replaces sobel_mag + mse in the LMSE loop of compute_sam_sid_lmse_caseB
 // (/root/reference/tools/run_codec.py:123-137, 341-346).  gx, gy are exact integers
-// (|g| <= 4*65535), gx^2+gy^2 < 2^38 is exact in float64 and sqrt is correctly rounded, so every
-// per-pixel term equals the reference's bit for bit; only the order of the final float64 sum
-// differs (block-ordered partials, reduced on the host).
+// (|g| <= 4*65535), gx^2+gy^2 < 2^38 is exact in float64 and the square root is faithfully rounded
+// (sobel_mag2), so every per-pixel term equals the reference's to the last bit or two; the order of the
+// final float64 sum differs (block-ordered partials, reduced on the host).
 //
-// BSQ only (the host transposes BIP cubes first).  Shared-memory tiled: a block stages a
-// (32+2) x (32+2) tile of both cubes once and every sample is read from HBM ~1.13 times.
+// BSQ: shared-memory tiled, a block stages a (32+2) x (32+2) tile of both cubes once and every sample is
+// read from HBM ~1.13 times.  BIP (16-bit samples, even band count): no transposition -- a thread owns one
+// 32-bit word of the spectrum (two bands), so a warp's loads are the contiguous spectrum of one pixel, and
+// marches along x over two image rows with the 3x3 window kept in registers as separable column terms
+// (vertical [1,2,1] sums and top-bottom differences of the last three columns).
 
 #include "dm_common.cuh"
 
@@ -17,6 +20,32 @@ namespace {
 
 constexpr int kSobBlocks = 296;   // partial slots per band (fixed: layout must not depend on the device)
 constexpr int TW = 32, TH = 32;
+
+// |grad| = sqrt(gx^2 + gy^2) for integer gradients (|g| <= 4*65535).  The sum of squares is an exact
+// float64 (< 2^38).  The square root is a BRANCH-FREE Goldschmidt iteration from the float32 MUFU.RSQ seed
+// (two coupled steps, then Markstein's final fma correction with the exact residual): faithfully rounded
+// (observed identical to __dsqrt_rn), and -- unlike the library routine, whose slow-path branch fences
+// every call -- the eight independent roots a thread needs per step interleave in the FP64 pipe.
+// The kernel is issue bound (ncu: 105 instructions per sample pair before this form, FP64 pipe 48 %), so
+// the helper is written for instruction count: native int->double conversions, the bare MUFU.RSQ.
+__device__ __forceinline__ double sobel_mag2(int gx, int gy) {
+  // int -> double without the conversion unit (I2F.F64 runs at a fraction of the FP64 rate and made this
+  // kernel 20 % slower): 2^52 + 2^31 + g as raw bits, minus the bias (exact)
+  const double fx = __hiloint2double(0x43300000, gx ^ 0x80000000) - 4503601774854144.0;
+  const double fy = __hiloint2double(0x43300000, gy ^ 0x80000000) - 4503601774854144.0;
+  const double s = fma(fx, fx, fy * fy);
+  const float gxf = (float)gx, gyf = (float)gy;              // exact (|g| < 2^24); the seed needs ~20 bits only
+  float yf;
+  // s == 0: the clamp keeps the seed finite, g = s * y = 0 and every later step stays 0 (no select needed)
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(fmaxf(fmaf(gxf, gxf, gyf * gyf), 1e-30f)));
+  const double y = (double)yf;
+  double g = s * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  return fma(fma(-g, g, s), h, g);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -85,6 +114,106 @@ sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   }
 }
 
+
+// ---- BIP ------------------------------------------------------------------------------------------
+constexpr int kBipThreads = 192;      // groups of WPpad threads (WPpad = words per pixel rounded up to a warp)
+constexpr int kBipCols = 30;          // columns per work item (a multiple of the 3-column trip); an item is two image rows x kBipCols columns
+
+template <int DT>
+struct ColTerms {                     // separable Sobel terms of one image column, two output rows, two bands
+  int v[2][2], d[2][2];               // [output row][band]:  v = p(y-1) + 2 p(y) + p(y+1),  d = p(y-1) - p(y+1)
+  __device__ __forceinline__ void set(const uint32_t (&w)[4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int p0 = sample16<DT>(w[0], h), p1 = sample16<DT>(w[1], h), p2 = sample16<DT>(w[2], h), p3 = sample16<DT>(w[3], h);
+      v[0][h] = p0 + 2 * p1 + p2; d[0][h] = p0 - p2;
+      v[1][h] = p1 + 2 * p2 + p3; d[1][h] = p1 - p3;
+    }
+  }
+};
+
+
+template <int DT>
+__global__ void __launch_bounds__(kBipThreads, 2)
+sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restrict__ tst, int wp, int wpad, int64_t width,
+                      int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows, double* out) {
+  __shared__ double red[kBipThreads][2];
+  const int groups = kBipThreads / wpad;
+  const int grp = threadIdx.x / wpad, w = threadIdx.x - grp * wpad;
+  const bool active = grp < groups && w < wp;
+  const int64_t nrows = row_end - row_begin;
+  const int64_t items_x = (width + kBipCols - 1) / kBipCols, items_y = (nrows + 1) / 2;
+  const int64_t nitems = items_x * items_y;
+  double acc0 = 0.0, acc1 = 0.0;
+  if (active) {
+    for (int64_t it = (int64_t)blockIdx.x * groups + grp; it < nitems; it += (int64_t)gridDim.x * groups) {
+      const int64_t y0 = row_begin + (it / items_x) * 2, c0 = (it % items_x) * kBipCols;
+      const int64_t c1 = c0 + kBipCols < width ? c0 + kBipCols : width;
+      const bool two = y0 + 1 < row_end;
+      // the four window rows, clamped to the IMAGE (np.pad mode="edge"), as buffer row offsets in words
+      int64_t ro[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int64_t ir = img_row0 + y0 + k - 1;
+        ir = ir < 0 ? 0 : (ir >= img_rows ? img_rows - 1 : ir);
+        ro[k] = (ir - img_row0) * width * wp + w;
+      }
+      // raw words of one column (four window rows, both cubes); loads are issued one column AHEAD of their
+      // use so that their latency hides behind the previous column's square roots
+      auto fetch = [&](int64_t c, uint32_t (&wa)[4], uint32_t (&wr)[4]) {
+        c = c < 0 ? 0 : (c >= width ? width - 1 : c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { wa[k] = __ldg(ref + ro[k] + c * wp); wr[k] = __ldg(tst + ro[k] + c * wp); }
+      };
+      auto emit = [&](const ColTerms<DT>& aL, const ColTerms<DT>& aC, const ColTerms<DT>& aR,
+                      const ColTerms<DT>& rL, const ColTerms<DT>& rC, const ColTerms<DT>& rR, bool live) {
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double ma = sobel_mag2(aL.v[o][h] - aR.v[o][h], aL.d[o][h] + 2 * aC.d[o][h] + aR.d[o][h]);
+            const double mr = sobel_mag2(rL.v[o][h] - rR.v[o][h], rL.d[o][h] + 2 * rC.d[o][h] + rR.d[o][h]);
+            const double e = __dsub_rn(ma, mr);
+            const double t = (live && (o == 0 || two)) ? __dmul_rn(e, e) : 0.0;   // column past the item / row past the strip
+            if (h == 0) acc0 += t; else acc1 += t;
+          }
+        }
+      };
+      ColTerms<DT> a0, a1, a2, r0, r1, r2;
+      uint32_t wa[4], wr[4], na[4], nr[4];
+      fetch(c0 - 1, wa, wr); a0.set(wa); r0.set(wr);
+      fetch(c0, wa, wr); a1.set(wa); r1.set(wr);
+      fetch(c0 + 1, wa, wr);                                   // column x+1 of the first output column, in flight
+      // one output column: fetch the column after next first, then consume the fetched one as the window's
+      // right edge (three columns per trip: the window rotates by renaming; a six-column trip that also
+      // renames the raw buffers doubles the code and was 20 % slower)
+#define DM_SOBEL_STEP(L_, C_, R_, x_)                                                   \
+      do {                                                                              \
+        fetch((x_) + 2, na, nr);                                                        \
+        a##R_.set(wa); r##R_.set(wr);                                                   \
+        emit(a##L_, a##C_, a##R_, r##L_, r##C_, r##R_, (x_) < c1);                      \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) { wa[k] = na[k]; wr[k] = nr[k]; } \
+      } while (0)
+      // the last trip may run one or two columns past the item: their (clamped) loads are harmless and
+      // their terms are dropped -- cheaper than a second copy of the step code for the tail
+      for (int64_t x = c0; x < c1; x += 3) {
+        DM_SOBEL_STEP(0, 1, 2, x);
+        DM_SOBEL_STEP(1, 2, 0, x + 1);
+        DM_SOBEL_STEP(2, 0, 1, x + 2);
+      }
+#undef DM_SOBEL_STEP
+    }
+  }
+  red[threadIdx.x][0] = acc0; red[threadIdx.x][1] = acc1;
+  __syncthreads();
+  if (threadIdx.x < wp) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int gi = 0; gi < groups; ++gi) { t0 += red[gi * wpad + threadIdx.x][0]; t1 += red[gi * wpad + threadIdx.x][1]; }
+    out[(int64_t)(2 * threadIdx.x) * kSobBlocks + blockIdx.x] = t0;
+    out[(int64_t)(2 * threadIdx.x + 1) * kSobBlocks + blockIdx.x] = t1;
+  }
+}
+
 }  // namespace
 
 int sobel_nblocks() { return kSobBlocks; }
@@ -92,13 +221,28 @@ int sobel_nblocks() { return kSobBlocks; }
 int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows,
                  double* out, cudaStream_t s) {
   if (!p.ref || !p.tst || !out) return fail(DM_EARG, "dm_sobel_lmse: null pointer");
-  if (p.layout != DM_BSQ) return fail(DM_EUNSUPPORTED, "dm_sobel_lmse: BSQ only (transpose with dm_bip_to_bsq)");
+  if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_sobel_lmse: bad layout");
+  if (p.layout == DM_BIP && (p.dtype == DM_U8 || p.bands % 2 != 0 || p.bands > 2 * kBipThreads ||
+                             (reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) % 4 != 0))
+    return fail(DM_EUNSUPPORTED, "dm_sobel_lmse: BIP needs 16-bit samples, an even band count and 4-byte aligned cubes "
+                                 "(otherwise transpose with dm_bip_to_bsq)");
   if (p.bands <= 0 || p.bands > 65535 || p.width <= 0) return fail(DM_EARG, "dm_sobel_lmse: bad geometry");
   if (row_begin < 0 || row_end > p.rows || row_begin > row_end || img_row0 < 0 || img_row0 + p.rows > img_rows)
     return fail(DM_EARG, "dm_sobel_lmse: bad row range");
   // halo rows must be present unless the strip touches the image border
   if ((row_begin == 0 && img_row0 > 0) || (row_end == p.rows && img_row0 + p.rows < img_rows))
     return fail(DM_EARG, "dm_sobel_lmse: strip lacks its halo row");
+  if (p.layout == DM_BIP) {
+    const int wp = (int)(p.bands / 2), wpad = (wp + 31) / 32 * 32;
+    if (p.dtype == DM_I16)
+      sobel_lmse_bip_kernel<DM_I16><<<kSobBlocks, kBipThreads, 0, s>>>(static_cast<const uint32_t*>(p.ref), static_cast<const uint32_t*>(p.tst),
+                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, out);
+    else
+      sobel_lmse_bip_kernel<DM_U16><<<kSobBlocks, kBipThreads, 0, s>>>(static_cast<const uint32_t*>(p.ref), static_cast<const uint32_t*>(p.tst),
+                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, out);
+    DM_LAUNCH_CHECK("sobel_lmse_bip");
+    return DM_OK;
+  }
   const dim3 grid(kSobBlocks, (unsigned)p.bands);
 #define DM_SOBEL(T)                                                                                          \
   sobel_lmse_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(p.ref), static_cast<const T*>(p.tst),      \

@@ -72,6 +72,37 @@ __device__ __forceinline__ double sid_term(double ap, double rp) {
   return (ap - rp) * L;
 }
 
+// atanh series coefficients in constant memory: FP64 instructions take them as constant-bank operands
+// (as literals every use costs two uniform moves)
+__constant__ double kAtanhC[8] = {1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0, 1.0, 2e-15, 1e-15};
+
+// fast path of one SID term; *slow is set when |d/s| >= 0.05 and the caller must take log()
+__device__ __forceinline__ double sid_term_fast(double ap, double rp, bool* slow) {
+  const double d = ap - rp, sden = (ap + rp) + kAtanhC[6];
+  float qf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(qf) : "f"((float)sden));      // ~2^-23 relative (sden >= 2e-15: no denormals)
+  double q = (double)qf;
+  q = fma(fma(-sden, q, kAtanhC[5]), q, q);                  // Newton: 2^-46
+  q = fma(fma(-sden, q, kAtanhC[5]), q, q);                  // 2^-92 -> rounding only
+  const double z = d * q;
+  *slow = fabs(z) >= 0.05;
+  const double z2 = z * z;
+  double pz = kAtanhC[0];
+  pz = fma(pz, z2, kAtanhC[1]);
+  pz = fma(pz, z2, kAtanhC[2]);
+  pz = fma(pz, z2, kAtanhC[3]);
+  pz = fma(pz, z2, kAtanhC[4]);
+  pz = fma(pz, z2, kAtanhC[5]);
+  return (d + d) * (z * pz);
+}
+
+// one SID term: the fast form, log() only where the series does not apply
+__device__ __forceinline__ double sid_term_auto(double ap, double rp) {
+  bool slow;
+  const double t = sid_term_fast(ap, rp, &slow);
+  return slow ? sid_term(ap, rp) : t;
+}
+
 // thread per pixel; bands at stride sb (BSQ: coalesced across the warp for every band)
 template <typename T>
 __global__ void __launch_bounds__(kSpecThreads)
@@ -125,7 +156,7 @@ spectral_pixel(SpecArgs g) {
         double t = 0.0;
         for (int b = 0; b < B; ++b) {
           const int a = ld(ref, base + b * g.sb), r = ld(tst, base + b * g.sb);
-          t += sid_term(((double)(a - amin) + 1e-12) * iSA, ((double)(r - rmin) + 1e-12) * iSR);
+          t += sid_term_auto(((double)(a - amin) + 1e-12) * iSA, ((double)(r - rmin) + 1e-12) * iSR);
         }
         s_sid += t;
       }
@@ -213,7 +244,7 @@ spectral_warp_bip(SpecArgs g) {
         double t = 0.0;
         for (int b = lane; b < B; b += 32) {
           const int a = ld(ref, base + b), r = ld(tst, base + b);
-          t += sid_term(((double)(a - amin) + 1e-12) * iSA, ((double)(r - rmin) + 1e-12) * iSR);
+          t += sid_term_auto(((double)(a - amin) + 1e-12) * iSA, ((double)(r - rmin) + 1e-12) * iSR);
         }
         t = warp_sum_f64(t);
         if (lane == 0) s_sid += t;
@@ -229,6 +260,114 @@ spectral_warp_bip(SpecArgs g) {
   }
   if (g.hist8_g && hg[tid]) atomic_add_i64(g.hist8_g + tid, hg[tid]);
   if (g.hist8_z && hz[tid]) atomic_add_i64(g.hist8_z + tid, hz[tid]);
+}
+
+
+// BIP, 16-bit samples, SAM / SID only (no error planes): one warp per pixel with the spectrum held in
+// REGISTERS as 32-bit words (two bands per lane and load, 128 contiguous bytes per warp load), so the
+// second sweep SID needs (after the minimum and the sum are known) re-reads nothing.  The SID term is
+// evaluated branch-free in the common case:  with d = ap - rp and s = ap + rp + 2e-15,
+//   ap*ln(a/r) + rp*ln(r/a) = d * ln(a/r) = d * 2 atanh(d / s)
+// (a = ap + 1e-15, r = rp + 1e-15: a - r = d and a + r = s up to one rounding), the quotient through a
+// float32 reciprocal seed and two Newton steps instead of a double division (whose slow-path branch
+// fences the library routine).  |d/s| >= 0.05 (large relative errors, typically dark bands at high
+// compression) takes log() in a second, warp-uniformly guarded step.
+template <int DT, int NWL>
+__global__ void __launch_bounds__(kSpecThreads)
+spectral_warp_bip16(SpecArgs g) {
+  __shared__ double red[3][kSpecThreads / 32];
+  const uint32_t* ref = static_cast<const uint32_t*>(g.ref);
+  const uint32_t* tst = static_cast<const uint32_t*>(g.tst);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = (int)g.bands, WPX = B >> 1;
+  double s_acos = 0.0, s_sid = 0.0, s_n = 0.0;     // meaningful in lane 0
+  const int64_t wstride = (int64_t)gridDim.x * (kSpecThreads / 32);
+  for (int64_t p = (int64_t)blockIdx.x * (kSpecThreads / 32) + warp; p < g.npix; p += wstride) {
+    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
+    if (!(v & DM_VALID_SPECTRAL)) continue;
+    const int64_t base = p * (int64_t)WPX;
+    uint32_t x[NWL], y[NWL];
+#pragma unroll
+    for (int j = 0; j < NWL; ++j) {
+      const int idx = lane + 32 * j;
+      if (idx < WPX) { x[j] = __ldg(ref + base + idx); y[j] = __ldg(tst + base + idx); }
+      else { x[j] = 0; y[j] = 0; }
+    }
+    int sa = 0, sr = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
+    long long dot = 0, na2 = 0, nr2 = 0;
+#pragma unroll
+    for (int j = 0; j < NWL; ++j) {
+      if (lane + 32 * j < WPX) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int a = sample16<DT>(x[j], h), r = sample16<DT>(y[j], h);
+          sa += a; sr += r; amin = min(amin, a); rmin = min(rmin, r);
+          if (g.want_sam) { dot += (long long)a * r; na2 += (long long)a * a; nr2 += (long long)r * r; }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+      rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    }
+    if (lane == 0) s_n += 1.0;
+    if (g.want_sam) {
+      dot = warp_sum_ll(dot); na2 = warp_sum_ll(na2); nr2 = warp_sum_ll(nr2);
+      if (lane == 0) {
+        const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
+        const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
+        double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
+        c = fmin(1.0, fmax(-1.0, c));
+        s_acos += acos(c);
+      }
+    }
+    if (g.want_sid) {
+      // Ap = (a - amin + 1e-12) / sum_b(a - amin + 1e-12); the integer part of the sum is exact
+      const double SA = (double)((long long)sa - (long long)B * amin) + (double)B * 1e-12;
+      const double SR = (double)((long long)sr - (long long)B * rmin) + (double)B * 1e-12;
+      const double iSA = 1.0 / SA, iSR = 1.0 / SR;
+      const double eA = 1e-12 * iSA, eR = 1e-12 * iSR;
+      double t = 0.0;
+      unsigned slow_mask = 0;                                 // bit 2j+h: this lane's sample needs log()
+#pragma unroll
+      for (int j = 0; j < NWL; ++j) {
+        const bool have = lane + 32 * j < WPX;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int a = sample16<DT>(x[j], h) - amin, r = sample16<DT>(y[j], h) - rmin;
+          bool slow;
+          const double term = sid_term_fast(fma((double)a, iSA, eA), fma((double)r, iSR, eR), &slow);
+          t += (have && !slow) ? term : 0.0;
+          slow_mask |= (have && slow) ? (1u << (2 * j + h)) : 0u;
+        }
+      }
+      if (__any_sync(0xffffffffu, slow_mask != 0)) {
+#pragma unroll
+        for (int j = 0; j < NWL; ++j) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (slow_mask & (1u << (2 * j + h))) {
+              const int a = sample16<DT>(x[j], h) - amin, r = sample16<DT>(y[j], h) - rmin;
+              const double ap = fma((double)a, iSA, eA), rp = fma((double)r, iSR, eR);
+              t += (ap - rp) * log((ap + 1e-15) / (rp + 1e-15));
+            }
+          }
+        }
+      }
+      t = warp_sum_f64(t);
+      if (lane == 0) s_sid += t;
+    }
+  }
+  if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
+  __syncthreads();
+  if (tid < 32 && g.acc) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    ordered_block_sum3(t0, t1, t2, g.ws, g.acc);
+  }
 }
 
 template <typename T>
@@ -263,6 +402,21 @@ int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_o
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
   g.want_sam = want_sam; g.want_sid = want_sid;
   g.acc = (want_sam || want_sid) ? spectral_acc : nullptr; g.ws = workspace;
+  // SAM / SID only on a 16-bit BIP cube: the register-resident warp kernel
+  if (bip && !errmax_out && !err8_g && !err8_z && (want_sam || want_sid) && p.dtype != DM_U8 && p.bands % 2 == 0 &&
+      p.bands <= 512 && ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 3) == 0) {
+    const int nwl = (int)((p.bands / 2 + 31) / 32);
+#define DM_SPEC16(DT)                                                                       \
+    do {                                                                                    \
+      if (nwl <= 3) spectral_warp_bip16<DT, 3><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);     \
+      else if (nwl <= 4) spectral_warp_bip16<DT, 4><<<kSpecBlocks, kSpecThreads, 0, s>>>(g); \
+      else spectral_warp_bip16<DT, 8><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);              \
+    } while (0)
+    if (p.dtype == DM_I16) DM_SPEC16(DM_I16); else DM_SPEC16(DM_U16);
+#undef DM_SPEC16
+    DM_LAUNCH_CHECK("spectral_bip16");
+    return DM_OK;
+  }
   switch (p.dtype) {
     case DM_U8: return run_spectral<uint8_t>(g, bip, s);
     case DM_U16: return run_spectral<uint16_t>(g, bip, s);

@@ -474,14 +474,24 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
         check(L.dm_spectral(C.byref(cp), _ptr(plane), *spectral_args,
                             1 if want.sam else 0, 1 if want.sid else 0, _ptr(P.spec), _ptr(ws), st))
     if want.lmse or want.ssim_gauss:
-        bsq = pair.as_bsq()
-        cb = bsq.c_pair()
         r0, r1 = rows if rows is not None else (0, pair.rows)
+        bsq = None
         if want.lmse:
             nb = L.dm_sobel_nblocks()
             buf = torch.empty(pair.bands * nb, dtype=torch.float64, device=dev)
-            check(L.dm_sobel_lmse(C.byref(cb), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st))
+            # BIP cubes of 16-bit samples go straight in (a thread owns two bands of the spectrum); the rest
+            # of the layouts are transposed first
+            rc = L.dm_sobel_lmse(C.byref(cp), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st) \
+                if pair.layout == "bip" else _lib.DM_EUNSUPPORTED
+            if rc == _lib.DM_EUNSUPPORTED:
+                bsq = pair.as_bsq()
+                cb = bsq.c_pair()
+                rc = L.dm_sobel_lmse(C.byref(cb), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st)
+            check(rc)
             P.lmse.add_(buf.view(pair.bands, nb).sum(dim=1))
+        if want.ssim_gauss and bsq is None:
+            bsq = pair.as_bsq()
+            cb = bsq.c_pair()
         if want.ssim_gauss:
             if data_range is None:
                 raise ValueError("ssim_gauss needs data_range (the peak L of the SSIM constants)")
