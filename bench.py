@@ -35,7 +35,7 @@ METRIC = "distortion-metric throughput (original+decoded image-pair bytes)"
 UNIT = "GB/s"
 BANDS, ROWS, WIDTH = 180, 1024, 1024
 PAIR_BYTES = 2 * 2 * BANDS * ROWS * WIDTH            # 754 974 720: SURVEY.md 8d algorithmic bytes
-COMBINE_BATCH = 8                                    # pairs per multi-GPU exchange (latency bound, a few KB per pair)
+COMBINE_BATCH = 64                                   # pairs per multi-GPU exchange (latency bound, 31.5 KB per pair; a sweep needs its results at its end)
 WORKLOAD = "Case B EnMAP 1024x1024x180 uint16 BIP cube pair per GPU: compute_metrics (per-band+global PSNR/SSIM/MAXAE) + SAM"
 
 
@@ -387,7 +387,8 @@ def main():
                                 "with one NCCL all-gather + dm_combine_partials on a side stream, overlapped with the next "
                                 "pairs' kernels; the timed region ends after the last combine") if world > 1 else "single GPU",
                    "kernels_per_step": ["dm_fused_bip (fused_ct_kernel<180>: per-band stats + per-pixel SAM from one read, "
-                                        "SAM partials reduced in-kernel), launched through engine.PreparedFused"]},
+                                        "SAM partials reduced in-kernel), launched through engine.PreparedFused; consecutive launches overlap "
+                                        "tail and ramp-up through programmatic dependent launch"]},
         "frac_of_hbm_peak": value / (world * peak),
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": UNIT,
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

@@ -645,6 +645,13 @@ fused_ct_kernel(FusedArgs g) {
   if (tid == 0) {
     for (int it = 0; it < kStages; ++it) issue_tile(it);
   }
+  // Programmatic dependent launch: a following launch of this kernel (run_ct sets the attribute) may
+  // start its CTAs as ours exit, instead of after the whole grid -- the tail of this launch (CTAs with
+  // one tile fewer, the last block's ordered reduction) then overlaps the next pair's first tiles.  The
+  // next launch only READS the cubes before its own griddepcontrol.wait (below, ahead of every global
+  // write), so nothing it does early can race with what is still running here.  Variants that write
+  // per-pixel planes do not trigger early: two launches may be given the same planes.
+  if (!ERR) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < G::BAND_WARPS) {
     // ------------------------------------------------------------------ band group
@@ -759,6 +766,9 @@ fused_ct_kernel(FusedArgs g) {
     else run(std::integral_constant<int, 1>());
 
     // ---- flush: per-band maxima and counts -> shared, then one thread per band -> global
+    // (the preceding launch must have finished before anything global is written: no-op unless this
+    // launch was started early through programmatic dependent launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (my_tiles > 0 && !(dbg & 2)) {
 #pragma unroll
       for (int j = 0; j < MPW; ++j) {
@@ -824,6 +834,7 @@ fused_ct_kernel(FusedArgs g) {
     // are combined with one shuffle per partial; the float64 finish is batched over two visits
     // (lanes 0-15 keep the pixels of the even visit, lanes 16-31 those of the odd one) so that all
     // 32 lanes of the warp work in it.
+    if (ERR) asm volatile("griddepcontrol.wait;" ::: "memory");   // planes are written in the tile loop
     const int tg = tid - G::BAND_THREADS;             // 0..255
     const int grp = tg >> 7;                          // tile parity this group serves
     const int wq = (tg >> 5) & 3;                     // warp of the group: pixels 16wq .. 16wq+15
@@ -927,6 +938,7 @@ fused_ct_kernel(FusedArgs g) {
     }
     if ((visit & 1) && hl == 0 && !(dbg & 4)) finish();      // pixels of an unpaired last visit
     __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // see the band group's flush
     s_acos = warp_sum_f64(s_acos); s_n = warp_sum_f64(s_n);
     const int pw = warp - G::BAND_WARPS;
     if (lane == 0) { red[0][pw] = s_acos; red[2][pw] = s_n; }
@@ -1110,11 +1122,19 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
   if (sms < 0) return DM_ECUDA;
   int64_t grid = sms < kMaxPartialBlocks ? sms : kMaxPartialBlocks;
   if (grid > g.ntiles) grid = g.ntiles;
+  static const bool pdl = []() { const char* e = getenv("DM_NO_PDL"); return !(e && atoi(e)); }();
 #define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
   do {                                                                                                \
     auto k = fused_ct_kernel<BANDS, DT, MASK, ERR, MPW>;                                              \
     DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));      \
-    k<<<(unsigned)grid, G::THREADS, G::SMEM, s>>>(g);                                                 \
+    cudaLaunchConfig_t cfg = {};                                                                      \
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(G::THREADS);                              \
+    cfg.dynamicSmemBytes = G::SMEM; cfg.stream = s;                                                   \
+    cudaLaunchAttribute at[1];                                                                        \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                    \
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;                                   \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                 \
+    DM_CUDA(cudaLaunchKernelEx(&cfg, k, g));                                                          \
   } while (0)
   const bool err = g.errmax || g.err8_g || g.err8_z;
   if (dtype == DM_U16) {
