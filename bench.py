@@ -395,8 +395,10 @@ def main():
                      "algorithmic_bytes_per_launch": PAIR_BYTES,
                      "launch_ms": {dominant: dom_ms}, "isolated_launch_ms": {dominant: iso_ms},
                      "note": "launch_ms: CUDA events over the timed region on the launching stream / launches (the step is "
-                             "one launch, back to back); isolated_launch_ms: events around single launches queued behind "
-                             "a spin kernel (includes the kernel's ramp-up and tail on an otherwise idle GPU)"},
+                             "one launch; consecutive launches are chained by programmatic dependent launch, so the "
+                             "ramp-up of one overlaps the tail of the previous and this is the steady-state duration); "
+                             "isolated_launch_ms: events around single launches queued behind a spin kernel (includes "
+                             "the kernel's ramp-up and tail on an otherwise idle GPU)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
