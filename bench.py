@@ -324,28 +324,27 @@ def main():
             host.append((r.view(torch.uint16), d.view(torch.uint16)))
         torch.cuda.synchronize()
 
-        def e2e_step(i):
-            r, d = host[i % 2]
-            pair = DevicePair.from_arrays(r, d, "bip")
-            P = evaluate(pair, want)
-            if world > 1:
-                P.allreduce_()
-            hp = P.to_host()                      # device -> host read of the step's result
-            out = finish.finish_compute_metrics(_lib.DM_U16, hp.sums, hp.maxs)
-            out.update(finish.finish_spectral(float(hp.spec[0]), float(hp.spec[1]), float(hp.spec[2]), None, 1))
-            return out, hp
+        from image_compression_analysis_b200.engine import evaluate_host_pairs
+
+        def e2e_run(n):
+            """n pairs from pinned host memory through the public sweep API: every pair is uploaded, evaluated
+            (+ exchanged across ranks), read back and finished on the host; uploads of the next pair overlap."""
+            outs_, hp_ = [], None
+            for hp_ in evaluate_host_pairs((host[i % 2] for i in range(n)), want, layout="bip"):
+                o = finish.finish_compute_metrics(_lib.DM_U16, hp_.sums, hp_.maxs)
+                o.update(finish.finish_spectral(float(hp_.spec[0]), float(hp_.spec[1]), float(hp_.spec[2]), None, 1))
+                outs_.append(o)
+            return outs_, hp_
 
         e2e_steps = max(3, min(args.steps, 10))
-        for i in range(2):
-            e2e_step(i)
+        e2e_run(2)
         barrier()
-        t0 = time.perf_counter()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(e2e_steps):
-            out, hp = e2e_step(i)
+        results, hp = e2e_run(e2e_steps)
         b.record()
         barrier()
+        assert len(results) == e2e_steps and results[-1]["max_abs_err"] == 3
         ms_e2e = a.elapsed_time(b)
         te = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -355,7 +354,8 @@ def main():
         e2e = {"value": world * PAIR_BYTES * e2e_steps / (ms_e2e * 1e-3) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": PAIR_BYTES, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": ms_e2e / e2e_steps,
-               "api": "engine.DevicePair.from_arrays(pinned host cubes) -> evaluate -> Partials.to_host -> finish.*"}
+               "api": "engine.evaluate_host_pairs(pinned host cubes) [upload of pair i+1 overlaps the kernels, exchange, "
+                      "read-back and host finish of pair i] -> finish.*"}
 
     if rank != 0:
         if world > 1:

@@ -520,3 +520,24 @@ def test_nodata_180_bands_vs_oracle(dtype, nd, with_valid, ref_only):
     torch.cuda.synchronize()
     assert np.array_equal(P.planes["err8_g"].cpu().numpy().reshape(H, W), o["err8_g"])
     assert np.array_equal(P.planes["err8_z"].cpu().numpy().reshape(H, W), o["err8_z"])
+
+
+def test_evaluate_host_pairs_matches_pair_by_pair():
+    """The pipelined sweep of pinned host pairs yields, in order, what evaluate() + to_host() yields per pair."""
+    import torch
+    from image_compression_analysis_b200 import synth
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate, evaluate_host_pairs
+    want = Want(stats=True, sam=True)
+    host, ref_out = [], []
+    for seed in range(5):
+        ref, dec = synth.case_b_pair(seed=40 + seed, bands=180, height=16, width=40, amp=1 + seed, layout="bsq")
+        r = torch.from_numpy(np.ascontiguousarray(np.moveaxis(ref, 0, -1)).view(np.int16)).pin_memory()
+        d = torch.from_numpy(np.ascontiguousarray(np.moveaxis(dec, 0, -1)).view(np.int16)).pin_memory()
+        host.append((r.view(torch.uint16), d.view(torch.uint16)))
+        ref_out.append(evaluate(DevicePair.from_arrays(r.view(torch.uint16), d.view(torch.uint16), "bip"), want).to_host())
+    got = list(evaluate_host_pairs(iter(host), want, layout="bip"))
+    assert len(got) == len(ref_out)
+    for g, w in zip(got, ref_out):
+        assert np.array_equal(g.isum, w.isum) and np.array_equal(g.imax, w.imax)
+        assert np.array_equal(g.fsum.view(np.int64), w.fsum.view(np.int64))       # same kernels, same order: bit-identical
+    assert list(evaluate_host_pairs(iter([]), want)) == []
