@@ -541,3 +541,65 @@ def test_evaluate_host_pairs_matches_pair_by_pair():
         assert np.array_equal(g.isum, w.isum) and np.array_equal(g.imax, w.imax)
         assert np.array_equal(g.fsum.view(np.int64), w.fsum.view(np.int64))       # same kernels, same order: bit-identical
     assert list(evaluate_host_pairs(iter([]), want)) == []
+
+
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_row_strips_with_halos_match_single_shot(layout, world):
+    """the image cut into row strips (1 halo row for Sobel, 5 for the Gaussian SSIM, replicated
+    at the cuts) and evaluated strip by strip gives the single-shot result: integers exactly, float sums to
+    rounding -- and both agree with the oracle.  Covers the BIP Sobel kernel's strip arguments."""
+    from image_compression_analysis_b200 import finish, sharding, synth
+    from image_compression_analysis_b200.engine import Want
+    from oracle import distortion_oracle as orc
+    B, H, W = 6, 67, 45
+    ref, dec = synth.case_b_pair(seed=77, bands=B, height=H, width=W, amp=5, layout="bsq")
+    if layout == "bip":
+        cube_r, cube_d = np.ascontiguousarray(np.moveaxis(ref, 0, -1)), np.ascontiguousarray(np.moveaxis(dec, 0, -1))
+        cut = sharding.cut_bip
+    else:
+        cube_r, cube_d, cut = ref, dec, sharding.cut_bsq
+    want = Want(stats=True, sam=True, sid=True, lmse=True, ssim_gauss=True)
+    L = 4095.0
+    tot = None
+    for s in sharding.strips(H, world, halo=sharding.HALO_SSIM):
+        P = sharding.evaluate_strip(cut(cube_r, s), cut(cube_d, s), s, H, layout, want, data_range=L, reduce=False)
+        h = P.to_host()
+        if tot is None:
+            tot = h
+        else:
+            tot.isum += h.isum
+            tot.imax = np.maximum(tot.imax, h.imax)
+            tot.fsum += h.fsum
+    got = finish.finish_compute_metrics(1, tot.sums, tot.maxs)
+    got.update(finish.finish_spectral(float(tot.spec[0]), float(tot.spec[1]), float(tot.spec[2]), tot.lmse, H * W))
+    got.update(finish.finish_ssim_gauss(tot.ssimw_sum, tot.ssimw_cnt))
+    want_d = orc.compute_metrics(ref, dec, extras=False)
+    want_d.update(orc.compute_sam_sid_lmse_caseB(ref, dec))
+    want_d.update(orc.ssim_gaussian(ref, dec, L))
+    for k, w in want_d.items():
+        if isinstance(w, np.ndarray):
+            continue
+        if isinstance(w, (int, np.integer)):
+            assert got[k] == int(w), (k, got[k], w)
+        else:
+            assert _close(got[k], w), (k, got[k], w)
+
+
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+def test_lmse_flat_and_zero_images(layout):
+    """Zero gradients everywhere (the branch-free square root must return 0, not NaN) and a pair whose
+    gradients differ in one pixel only."""
+    import image_compression_analysis_b200 as dm
+    from oracle import distortion_oracle as orc
+    B, H, W = 4, 12, 20
+    flat = np.full((B, H, W), 1234, np.uint16)
+    zero = np.zeros((B, H, W), np.uint16)
+    spike = flat.copy()
+    spike[1, 5, 7] = 60000
+    for a, b in ((flat, flat), (zero, zero), (flat, zero), (flat, spike)):
+        ra, rb = (a, b) if layout == "bsq" else (np.ascontiguousarray(np.moveaxis(a, 0, -1)), np.ascontiguousarray(np.moveaxis(b, 0, -1)))
+        got = dm.compute_sam_sid_lmse_caseB_arrays(ra, rb, layout=layout)
+        want = orc.compute_sam_sid_lmse_caseB(a, b)
+        assert not math.isnan(got["lmse"]) and _close(got["lmse"], want["lmse"]), (got, want)
+        assert _close(got["sid"], want["sid"]) and _close(got["sam_deg"], want["sam_deg"]), (got, want)
