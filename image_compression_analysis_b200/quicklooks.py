@@ -20,6 +20,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import finish
+from ._lib import DM_VALID_QUICKLOOK
 from .engine import DevicePair, Want, evaluate, to_device
 from .raster_io import explicit_mask, open_raster, uint8_dtype
 
@@ -63,7 +64,7 @@ def stretch_params_cube(cube_t, np_dtype, layout, B, H, W, nodata=None, extra_ma
     import torch
     from . import adjacent
     plane = _quicklook_plane(cube_t, np_dtype, layout, B, H, W, nodata)
-    bit = engine_bits()
+    bit = DM_VALID_QUICKLOOK
     if extra_mask is not None:              # explicit alpha / .msk mask: fold it into the plane
         m = to_device(np.asarray(extra_mask) > 0).reshape(-1)
         plane = (m * bit) if plane is None else (plane & (m * bit))
@@ -83,11 +84,6 @@ def stretch_params_cube(cube_t, np_dtype, layout, B, H, W, nodata=None, extra_ma
                 hi = lo + 1.0
         params.append((float(lo), float(hi)))
     return params
-
-
-def engine_bits() -> int:
-    from ._lib import DM_VALID_QUICKLOOK
-    return DM_VALID_QUICKLOOK
 
 
 def rgb_8bit_cube(cube_t, np_dtype, layout, B, H, W, params, rgb_order=RGB_ORDER):
@@ -252,37 +248,36 @@ def write_error_max8(a_path, b_path, out_path_base, err_max_global=255, err_max_
     Returns: (global_path, zoom_path or None)
     """
     from .ingest import load_pair
-    if True:
-        try:
-            pair, info = load_pair(a_path, b_path)      # read once per rep, shared with compute_metrics
-        except AssertionError:
-            raise AssertionError("Dims/band count must match")
-        res = error_max8_pair(pair, err_max_global, err_max_zoom, pct, a_mask=info["ref_mask"], b_mask=info["tst_mask"])
-        meta = dict(info["ref_meta"])
-        meta.update(driver="GTiff", count=1, dtype=uint8_dtype(), photometric="MINISBLACK", tiled=True,
-                    blockxsize=512, blockysize=512, compress="DEFLATE")
-        meta.pop("nodata", None)
-        out_base = Path(out_path_base)
-        out_base.parent.mkdir(parents=True, exist_ok=True)
-        mask255 = res["valid"].astype(np.uint8) * 255
+    try:
+        pair, info = load_pair(a_path, b_path)      # read once per rep, shared with compute_metrics
+    except AssertionError:
+        raise AssertionError("Dims/band count must match")
+    res = error_max8_pair(pair, err_max_global, err_max_zoom, pct, a_mask=info["ref_mask"], b_mask=info["tst_mask"])
+    meta = dict(info["ref_meta"])
+    meta.update(driver="GTiff", count=1, dtype=uint8_dtype(), photometric="MINISBLACK", tiled=True,
+                blockxsize=512, blockysize=512, compress="DEFLATE")
+    meta.pop("nodata", None)
+    out_base = Path(out_path_base)
+    out_base.parent.mkdir(parents=True, exist_ok=True)
+    mask255 = res["valid"].astype(np.uint8) * 255
 
-        def emit(plane, cap, mean, std):
-            out = out_base.with_name(out_base.stem + f"_ERR8_0_{cap}.tif")
-            with open_raster(out.as_posix(), "w", **meta) as dst:
-                dst.write(plane[None, ...])
-                try:
-                    dst.write_mask(mask255)
-                except Exception:
-                    pass
-                dst.update_tags(STATISTICS_MINIMUM="0", STATISTICS_MAXIMUM="255", STATISTICS_MEAN=str(float(mean)),
-                                STATISTICS_STDDEV=str(float(std)), PIXEL_MINIMUM="0", PIXEL_MAXIMUM="255")
-            return out
+    def emit(plane, cap, mean, std):
+        out = out_base.with_name(out_base.stem + f"_ERR8_0_{cap}.tif")
+        with open_raster(out.as_posix(), "w", **meta) as dst:
+            dst.write(plane[None, ...])
+            try:
+                dst.write_mask(mask255)
+            except Exception:
+                pass
+            dst.update_tags(STATISTICS_MINIMUM="0", STATISTICS_MAXIMUM="255", STATISTICS_MEAN=str(float(mean)),
+                            STATISTICS_STDDEV=str(float(std)), PIXEL_MINIMUM="0", PIXEL_MAXIMUM="255")
+        return out
 
-        out_g = emit(res["err8_g"], res["cap_g"], res["mean_g"], res["std_g"])
-        out_z = None
-        if err_max_zoom is not None:
-            out_z = emit(res["err8_z"], res["cap_z"], res["mean_z"], res["std_z"])
-        return out_g, out_z
+    out_g = emit(res["err8_g"], res["cap_g"], res["mean_g"], res["std_g"])
+    out_z = None
+    if err_max_zoom is not None:
+        out_z = emit(res["err8_z"], res["cap_z"], res["mean_z"], res["std_z"])
+    return out_g, out_z
 
 
 if __name__ == "__main__":

@@ -212,3 +212,52 @@ def test_c_abi_argument_errors():
     assert L.dm_diff1(None, None, _lib.DM_I16, 0, 0, 4, 16, 16, None) == _lib.DM_EARG
     assert L.dm_interleave(None, None, 2, 0, 1, 4, 4, 4, None) == _lib.DM_EARG
     assert b"null" in L.dm_last_error()
+
+
+def test_path_level_functions_on_real_files(tmp_path, monkeypatch):
+    """The reference-named entry points on REAL GeoTIFFs (built-in reader/writer, no rasterio):
+    stretch_params_from_baseline / write_rgb_8bit (quicklooks.py:51-109), write_truncated_copy /
+    make_scene_error_map (make_baseline_B.py:284-419), to_12in16 (make_baseline_A.py:137-170)."""
+    import sys
+    monkeypatch.delitem(sys.modules, "rasterio", raising=False)
+    from PIL import Image
+    from image_compression_analysis_b200 import baseline, geotiff, ingest, quicklooks as ql
+    ingest.clear_cache()
+    r = g("adj_rgb_i16_nodata")
+    cube, nd = r["cube"], _nodata(r)
+    B, H, W = cube.shape
+    src = tmp_path / "scene.tif"
+    with geotiff.open(src, "w", dtype="int16", count=B, width=W, height=H, tiled=True, blockxsize=64, blockysize=64,
+                      nodata=nd) as dst:
+        dst.write(cube)
+    order, pct = [int(i) for i in r["order"]], tuple(r["pct"])
+    params = ql.stretch_params_from_baseline(src, rgb_order=order, pct=pct)
+    assert np.array_equal(np.array(params), r["params"])
+    ql.write_rgb_8bit(src, tmp_path / "ql" / "rgb.tif", params, rgb_order=order)
+    with geotiff.open(tmp_path / "ql" / "rgb.tif") as d:
+        assert d.count == 3 and d.dtypes[0] == "uint8" and d.nodata is None
+        assert np.array_equal(d.read(), r["rgb"])
+    # 14-in-16 copy with nodata kept, then the scene error map against the original
+    t = g("adj_trunc_i16_k2")
+    with geotiff.open(tmp_path / "in16.tif", "w", dtype="int16", count=t["cube"].shape[0], width=t["cube"].shape[2],
+                      height=t["cube"].shape[1], nodata=_nodata(t)) as dst:
+        dst.write(t["cube"])
+    baseline.write_truncated_copy(tmp_path / "in16.tif", tmp_path / "out14.tif", int(t["k"][0]))
+    with geotiff.open(tmp_path / "out14.tif") as d:
+        assert np.array_equal(d.read(), t["out"]) and d.nodata == _nodata(t)
+    sc = g("adj_scene_i16_k2")
+    for name, arr in (("ref.tif", sc["ref"]), ("cmp.tif", sc["cmp"])):
+        with geotiff.open(tmp_path / name, "w", dtype="int16", count=arr.shape[0], width=arr.shape[2], height=arr.shape[1]) as dst:
+            dst.write(arr)
+    with geotiff.open(tmp_path / "mask.tif", "w", dtype="uint8", count=1, width=sc["mask"].shape[1], height=sc["mask"].shape[0]) as dst:
+        dst.write(sc["mask"].astype(np.uint8)[None])
+    for mode in ("mean", "p95"):
+        baseline.make_scene_error_map(tmp_path / "ref.tif", tmp_path / "cmp.tif", tmp_path / "mask.tif", "auto",
+                                      int(sc["k_bits"][0]), tmp_path / f"{mode}.png", err_mode=mode)
+        assert np.array_equal(np.array(Image.open(tmp_path / f"{mode}.png")), sc[f"img_{mode}_auto"])
+    a = g("adj_to12in16")
+    with geotiff.open(tmp_path / "a.tif", "w", dtype="uint16", count=4, width=a["cube"].shape[2], height=a["cube"].shape[1]) as dst:
+        dst.write(a["cube"])
+    baseline.to_12in16(tmp_path / "a.tif", tmp_path / "o" / "a12.tif")
+    with geotiff.open(tmp_path / "o" / "a12.tif") as d:
+        assert np.array_equal(d.read(), a["out"])
