@@ -64,28 +64,44 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   if (ncols > 0 && nrows > 0) {
     const int64_t tiles_x = (ncols + SW - 1) / SW, tiles_y = (nrows + SH - 1) / SH;
     const int64_t ntiles = tiles_x * tiles_y;
+    // Software pipeline over the tiles of this block: the (64 x 42) samples of both cubes of the NEXT tile are
+    // fetched into registers (one ref/tst pair per register, eleven per thread) right after the current
+    // tile has been staged, so that their DRAM latency passes during the two filter passes instead of in
+    // front of them.  Element e = threadIdx.x + 256 k of the tile is row e / 42, column e % 42; clamped
+    // indices are only reached by outputs that are discarded.
+    constexpr int NPRE = (IH * IW + 255) / 256;          // 11
+    uint32_t pre[NPRE];
+    auto fetch_tile = [&](int64_t t) {
+      const int64_t r0 = r_lo + (t / tiles_x) * SH, c0 = c_lo + (t % tiles_x) * SW;
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        const int lr = e / IW, lc = e - lr * IW;
+        int64_t r = r0 + lr - RAD, c = c0 + lc - RAD;
+        r = r < 0 ? 0 : (r >= buf_rows ? buf_rows - 1 : r);
+        c = c < 0 ? 0 : (c >= width ? width - 1 : c);
+        const uint32_t a = e < IH * IW ? (uint32_t)(uint16_t)A[r * width + c] : 0u;
+        const uint32_t b = e < IH * IW ? (uint32_t)(uint16_t)R[r * width + c] : 0u;
+        pre[k] = a | (b << 16);
+      }
+    };
+    if ((int64_t)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int64_t r0 = r_lo + (t / tiles_x) * SH, c0 = c_lo + (t % tiles_x) * SW;
       const int rows_here = (int)(r_hi - r0 < SH ? r_hi - r0 : SH), cols_here = (int)(c_hi - c0 < SW ? c_hi - c0 : SW);
       __syncthreads();
-      // stage: warp ty takes rows ty, ty+8, ...; lane = column (two columns for the first ten lanes).
-      // Clamped indices are only reached by outputs that are discarded.
-      {
-        int64_t ca = c0 + tx - RAD, cb = c0 + tx + 32 - RAD;
-        ca = ca < 0 ? 0 : (ca >= width ? width - 1 : ca);
-        cb = cb < 0 ? 0 : (cb >= width ? width - 1 : cb);
-#pragma unroll 4
-        for (int lr = ty; lr < IH; lr += 8) {
-          int64_t r = r0 + lr - RAD;
-          r = r < 0 ? 0 : (r >= buf_rows ? buf_rows - 1 : r);
-          const T* ar = A + r * width;
-          const T* rr = R + r * width;
-          xs[lr][tx] = (int)ar[ca];
-          ys[lr][tx] = (int)rr[ca];
-          if (tx < IW - 32) { xs[lr][tx + 32] = (int)ar[cb]; ys[lr][tx + 32] = (int)rr[cb]; }
+#pragma unroll
+      for (int k = 0; k < NPRE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        if (e < IH * IW) {
+          const int lr = e / IW, lc = e - lr * IW;
+          // (T)(...) restores the sample's sign for int16 cubes
+          xs[lr][lc] = (int)(T)(pre[k] & 0xffffu);
+          ys[lr][lc] = (int)(T)(pre[k] >> 16);
         }
       }
       __syncthreads();
+      if (t + gridDim.x < ntiles) fetch_tile(t + gridDim.x);
       // ---- pass H: item = (group of 4 output columns, row lr); 512 items, two per thread.  The ROW is
       // the fastest thread index: the lanes of a warp read the same columns of 32 rows (43 words apart)
       // and write the same columns of 32 plane rows (33 doubles apart) -- both strides odd, conflict free.

@@ -1,0 +1,26 @@
+"""Gaussian-SSIM kernel timing: Case-A tile (rotated) and the 10980^2 scene."""
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
+def mk(B, H, W, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    ref = torch.randint(0, 4096, (B, H, W), device="cuda", dtype=torch.int16, generator=g) * 16
+    tst = (ref + 16 * torch.randint(-3, 4, (B, H, W), device="cuda", dtype=torch.int16, generator=g)).clamp_(0, 32767)
+    return DevicePair(ref, tst, "uint16", "bsq", B, H, W)
+def t(fn, n=6):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); e1.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for name, B, H, W in (("caseA tile", 4, 1024, 1024), ("scene", 4, 10980, 10980)):
+    pair = mk(B, H, W, 1)
+    P = Partials.allocate(B, 0, pair.ref.device, "uint16")
+    us = t(lambda: evaluate(pair, Want(stats=False, ssim_gauss=True), out=P, data_range=4095.0))
+    print(f"{name:12s} ssim_gauss {us:9.1f} us  {4*B*H*W/us/1e3:8.1f} GB/s", flush=True)
+    del pair
+    torch.cuda.empty_cache()
