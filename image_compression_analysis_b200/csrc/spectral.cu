@@ -280,19 +280,28 @@ spectral_warp_bip16(SpecArgs g) {
   const uint32_t* tst = static_cast<const uint32_t*>(g.tst);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = (int)g.bands, WPX = B >> 1;
-  double s_acos = 0.0, s_sid = 0.0, s_n = 0.0;     // meaningful in lane 0
+  double s_acos = 0.0, s_n = 0.0;                  // meaningful in lane 0
+  double s_sid = 0.0;                              // per LANE: SID is a plain sum over pixels and bands, so the
+                                                   // lanes' shares meet once, at the end of the kernel
   const int64_t wstride = (int64_t)gridDim.x * (kSpecThreads / 32);
-  for (int64_t p = (int64_t)blockIdx.x * (kSpecThreads / 32) + warp; p < g.npix; p += wstride) {
-    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
-    if (!(v & DM_VALID_SPECTRAL)) continue;
+  uint32_t x[NWL], y[NWL], nx[NWL], ny[NWL];
+  auto fetch = [&](int64_t p, uint32_t (&a)[NWL], uint32_t (&b)[NWL]) {
     const int64_t base = p * (int64_t)WPX;
-    uint32_t x[NWL], y[NWL];
 #pragma unroll
     for (int j = 0; j < NWL; ++j) {
       const int idx = lane + 32 * j;
-      if (idx < WPX) { x[j] = __ldg(ref + base + idx); y[j] = __ldg(tst + base + idx); }
-      else { x[j] = 0; y[j] = 0; }
+      if (idx < WPX) { a[j] = __ldg(ref + base + idx); b[j] = __ldg(tst + base + idx); }
+      else { a[j] = 0; b[j] = 0; }
     }
+  };
+  int64_t p = (int64_t)blockIdx.x * (kSpecThreads / 32) + warp;
+  if (p < g.npix) fetch(p, nx, ny);
+  for (; p < g.npix; p += wstride) {
+#pragma unroll
+    for (int j = 0; j < NWL; ++j) { x[j] = nx[j]; y[j] = ny[j]; }
+    if (p + wstride < g.npix) fetch(p + wstride, nx, ny);        // the next pixel's spectrum, in flight during this one
+    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
+    if (!(v & DM_VALID_SPECTRAL)) continue;
     int sa = 0, sr = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
     long long dot = 0, na2 = 0, nr2 = 0;
 #pragma unroll
@@ -306,13 +315,9 @@ spectral_warp_bip16(SpecArgs g) {
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sa += __shfl_xor_sync(0xffffffffu, sa, o);
-      sr += __shfl_xor_sync(0xffffffffu, sr, o);
-      amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
-      rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-    }
+    // one REDUX per quantity instead of five shuffle steps
+    sa = __reduce_add_sync(0xffffffffu, sa); sr = __reduce_add_sync(0xffffffffu, sr);
+    amin = __reduce_min_sync(0xffffffffu, amin); rmin = __reduce_min_sync(0xffffffffu, rmin);
     if (lane == 0) s_n += 1.0;
     if (g.want_sam) {
       dot = warp_sum_ll(dot); na2 = warp_sum_ll(na2); nr2 = warp_sum_ll(nr2);
@@ -357,10 +362,10 @@ spectral_warp_bip16(SpecArgs g) {
           }
         }
       }
-      t = warp_sum_f64(t);
-      if (lane == 0) s_sid += t;
+      s_sid += t;
     }
   }
+  s_sid = warp_sum_f64(s_sid);
   if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
   __syncthreads();
   if (tid < 32 && g.acc) {
