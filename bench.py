@@ -386,7 +386,7 @@ def main():
                    "sharding": (f"row strips, one per GPU; the integer/float64 partials of every {COMBINE_BATCH} pairs are combined "
                                 "with one NCCL all-gather + dm_combine_partials on a side stream, overlapped with the next "
                                 "pairs' kernels; the timed region ends after the last combine") if world > 1 else "single GPU",
-                   "kernels_per_step": ["dm_fused_bip (fused_ct_kernel<180>: per-band stats + per-pixel SAM from one read, "
+                   "kernels_per_step": ["dm_fused_bip (fused_ct_kernel<180>, 23 band + 8 pixel warps: per-band stats + per-pixel SAM from one read, "
                                         "SAM partials reduced in-kernel), launched through engine.PreparedFused; consecutive launches overlap "
                                         "tail and ramp-up through programmatic dependent launch"]},
         "frac_of_hbm_peak": value / (world * peak),

@@ -603,3 +603,20 @@ def test_lmse_flat_and_zero_images(layout):
         want = orc.compute_sam_sid_lmse_caseB(a, b)
         assert not math.isnan(got["lmse"]) and _close(got["lmse"], want["lmse"]), (got, want)
         assert _close(got["sid"], want["sid"]) and _close(got["sam_deg"], want["sam_deg"]), (got, want)
+
+
+@pytest.mark.parametrize("variant", ["16", "0"])
+@pytest.mark.parametrize("args", [("uint16", 180, 37, 53, 5, False), ("uint16", 180, 64, 64, 65535, True),
+                                  ("int16", 180, 40, 41, 30000, True)])
+def test_fused_ct_both_band_warp_layouts(args, variant, monkeypatch):
+    """The 180-band kernel exists with 12 band warps (ldmatrix.x4, 96 registers) and with 23 (ldmatrix.x2, 64
+    registers); DM_FUSED_DEBUG bit 16 flips the default.  Both must match the oracle."""
+    monkeypatch.setenv("DM_FUSED_DEBUG", variant)
+    test_fused_bip_vs_oracle(*args)
+
+
+@pytest.mark.parametrize("variant", ["16", "0"])
+def test_nodata_180_bands_both_band_warp_layouts(variant, monkeypatch):
+    monkeypatch.setenv("DM_FUSED_DEBUG", variant)
+    test_nodata_180_bands_vs_oracle("int16", -32768, True, False)
+    test_nodata_180_bands_vs_oracle("uint16", 65535, True, False)
