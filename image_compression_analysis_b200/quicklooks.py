@@ -156,21 +156,28 @@ def error_max8_pair(pair: DevicePair, err_max_global=255, err_max_zoom=None, pct
         if m is not None:
             extra = np.asarray(m) > 0 if extra is None else (extra & (np.asarray(m) > 0))
 
-    def lut_for(cap, errmax_host):
+    def lut_for(cap, errmax_dev):
         if cap is not None:
             return finish.err8_lut(cap), int(round(float(cap)))
-        # percentile branch (quicklooks.py:137-146): unreachable from run_codec, kept for the CLI
-        e = errmax_host().astype(np.float32)
-        nz = e[e > 0]
-        if nz.size:
-            lo, hi = np.percentile(nz, pct)
+        # percentile branch (quicklooks.py:137-146): unreachable from run_codec, kept for the CLI.  The 2nd /
+        # 98th percentile of the non-zero errors comes from the exact value histogram of the uint16 error
+        # plane (dm_band_hist), like the RGB stretch; bin 0 is dropped (nz = e[e > 0]).
+        from . import adjacent
+        e = errmax_dev()
+        hist = adjacent.band_hist(e, "uint16", "bsq", 1, H, W, [0]).cpu().numpy()[0]
+        got = finish.percentiles_from_hist(hist[1:], 1, pct)
+        if got is None:
+            lo, hi = 0.0, 1.0
+        else:
+            # np.percentile hands the reference numpy float64 scalars, which make its float32 expression
+            # evaluate in float64 (NumPy 2 promotion); Python floats would keep it in float32
+            lo, hi = np.float64(got[0]), np.float64(got[1])
             if not np.isfinite(lo):
                 lo = 0.0
             if (not np.isfinite(hi)) or hi <= lo:
                 hi = lo + 1.0
-        else:
-            lo, hi = 0.0, 1.0
-        top = int(e.max()) if e.size else 0
+        nzb = np.nonzero(hist)[0]
+        top = int(nzb[-1]) if nzb.size else 0
         grid = np.arange(top + 1, dtype=np.int64).astype(np.float32)
         lut = (np.clip((grid - lo) / (hi - lo + 1e-9), 0, 1) * 255.0).astype(np.uint8)
         return lut, int(round(hi))
@@ -178,11 +185,12 @@ def error_max8_pair(pair: DevicePair, err_max_global=255, err_max_zoom=None, pct
     _cache = {}
 
     def errmax_host():
+        """uint16 plane of max_b |A - B| on the device (0 where invalid), explicit masks folded in."""
         if "e" not in _cache:
             P0 = evaluate(pair, Want(stats=False, errmax=True))
-            e = P0.planes["errmax"].cpu().numpy().view(np.uint16).reshape(H, W).copy()
+            e = P0.planes["errmax"]
             if extra is not None:
-                e[~extra] = 0
+                e = e * to_device(extra.reshape(-1)).to(e.dtype)
             _cache["e"] = e
         return _cache["e"]
 

@@ -346,7 +346,7 @@ def err8_lut(cap: int) -> np.ndarray:
     return e8.astype(np.uint8)
 
 
-def error_max8(ref: np.ndarray, tst: np.ndarray, err_max_global: int = 255,
+def error_max8(ref: np.ndarray, tst: np.ndarray, err_max_global: Optional[int] = 255,
                err_max_zoom: Optional[int] = None, *, ref_nodata=None, tst_nodata=None,
                ref_mask=None, tst_mask=None) -> Dict[str, object]:
     """Pixel content of write_error_max8 (quicklooks.py:123-205) for fixed caps.
@@ -362,7 +362,18 @@ def error_max8(ref: np.ndarray, tst: np.ndarray, err_max_global: int = 255,
     err[~valid] = 0.0                                                    # :134
 
     def scale(cap):
-        lo, hi = 0.0, float(cap)
+        if cap is None:                                                  # :137-146 (pct = (2, 98), the CLI's branch)
+            nz = err[err > 0]
+            if nz.size:
+                lo, hi = np.percentile(nz, (2, 98))
+                if not np.isfinite(lo):
+                    lo = 0.0
+                if (not np.isfinite(hi)) or hi <= lo:
+                    hi = lo + 1.0
+            else:
+                lo, hi = 0.0, 1.0
+        else:
+            lo, hi = 0.0, float(cap)
         e8 = np.clip((err - lo) / (hi - lo + 1e-9), 0, 1) * 255.0        # :149
         return e8.astype(np.uint8), int(round(hi))
 

@@ -620,3 +620,21 @@ def test_nodata_180_bands_both_band_warp_layouts(variant, monkeypatch):
     monkeypatch.setenv("DM_FUSED_DEBUG", variant)
     test_nodata_180_bands_vs_oracle("int16", -32768, True, False)
     test_nodata_180_bands_vs_oracle("uint16", 65535, True, False)
+
+
+@pytest.mark.parametrize("layout", ["bsq", "bip"])
+def test_error_max8_percentile_scaling(layout):
+    """err_max_global=None (quicklooks.py:137-146): the 2nd / 98th percentile of the non-zero errors from the
+    device histogram of the error plane, the reference's float64 evaluation of the stretch."""
+    from image_compression_analysis_b200 import quicklooks as ql
+    from oracle import distortion_oracle as orc
+    rng = np.random.default_rng(5)
+    ref = rng.integers(0, 4000, (6, 30, 41)).astype(np.uint16)
+    dec = np.clip(ref.astype(np.int64) + rng.integers(-40, 41, ref.shape), 0, 65535).astype(np.uint16)
+    dec[:, :4] = ref[:, :4]
+    for a, b in ((ref, dec), (ref, ref)):                      # identical pair: no non-zero error at all
+        want = orc.error_max8(a, b, None, 16)
+        ra, rb = (a, b) if layout == "bsq" else (np.ascontiguousarray(np.moveaxis(a, 0, -1)), np.ascontiguousarray(np.moveaxis(b, 0, -1)))
+        got = ql.error_max8_arrays(ra, rb, None, 16, layout=layout)
+        assert got["cap_g"] == want["cap_g"]
+        assert np.array_equal(got["err8_g"], want["err8_g"]) and np.array_equal(got["err8_z"], want["err8_z"])

@@ -70,3 +70,23 @@ def test_scalar_helpers():
     assert orc.psnr(a, a, 65535) == rc.psnr(a, a, 65535) == float("inf")
     assert orc.ssim_global(a, b, 4095) == rc.ssim_global(a, b, 4095)
     assert np.array_equal(orc.sobel_mag(a), rc.sobel_mag(a))
+
+
+def test_error_max8_percentile_branch_vs_reference(tmp_path):
+    """write_error_max8 with err_max_global=None (quicklooks.py:137-146, the CLI's percentile scaling)."""
+    from oracle import distortion_oracle as orc, rasterio_stub, reference_loader as rl
+    if not rl.available():
+        pytest.skip("reference tree not mounted")
+    ql = rl.quicklooks()
+    rng = np.random.default_rng(5)
+    ref = rng.integers(0, 4000, (5, 30, 41)).astype(np.uint16)
+    dec = np.clip(ref.astype(np.int64) + rng.integers(-40, 41, ref.shape), 0, 65535).astype(np.uint16)
+    dec[:, :4] = ref[:, :4]                                     # zero-error pixels are excluded from the percentiles
+    rasterio_stub.clear()
+    rasterio_stub.register("/mem/a.tif", ref)
+    rasterio_stub.register("/mem/b.tif", dec)
+    og, oz = ql.write_error_max8("/mem/a.tif", "/mem/b.tif", "/mem/out", err_max_global=None, err_max_zoom=16)
+    want = orc.error_max8(ref, dec, None, 16)
+    assert str(og).endswith(f"_ERR8_0_{want['cap_g']}.tif")
+    assert np.array_equal(rasterio_stub.fetch(og).data[0], want["err8_g"])
+    assert np.array_equal(rasterio_stub.fetch(oz).data[0], want["err8_z"])
