@@ -80,33 +80,38 @@ struct LutArgs {
   uint8_t* out;            // nsel x npix
 };
 
+// The 64 KB table of the block's channel sits in shared memory (a gather there costs bank conflicts only;
+// through L1 every divergent lane is a tag lookup); contiguous 16-bit bands are read 8 pixels per thread.
 template <typename T, int DT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 lut_bands_kernel(LutArgs g) {
+  extern __shared__ __align__(16) uint8_t slut[];               // 65536 bytes
   const int c = blockIdx.y;
   const T* src = static_cast<const T*>(g.data) + (int64_t)g.sel[c] * g.sb;
-  const uint8_t* lut = g.luts + (int64_t)c * 65536;
   uint8_t* out = g.out + (int64_t)c * g.npix;
-  // four pixels per thread: one 32-bit store
-  const int64_t nq = g.npix >> 2;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-    unsigned w = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned v = bin_of<DT>((unsigned)(uint16_t)src[(4 * q + j) * g.sp]);
-      w |= (unsigned)__ldg(lut + v) << (8 * j);
-    }
-    if ((reinterpret_cast<uintptr_t>(out) & 3) == 0) {
-      reinterpret_cast<unsigned*>(out)[q] = w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) out[4 * q + j] = (uint8_t)(w >> (8 * j));
-    }
+  {
+    const uint4* gl = reinterpret_cast<const uint4*>(g.luts + (int64_t)c * 65536);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) reinterpret_cast<uint4*>(slut)[i] = __ldg(gl + i);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (g.npix & 3)) {
-    const int64_t p = 4 * nq + threadIdx.x;
-    out[p] = __ldg(lut + bin_of<DT>((unsigned)(uint16_t)src[p * g.sp]));
+  __syncthreads();
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  int64_t done = 0;
+  if (sizeof(T) == 2 && g.sp == 1 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    const int64_t nv = g.npix >> 3;
+    for (int64_t i = tid; i < nv; i += nth) {
+      const uint4 v = ldg_stream16(reinterpret_cast<const uint4*>(src) + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t o[2] = {0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned bin = bin_of<DT>((w[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        o[j >> 2] |= (uint32_t)slut[bin] << (8 * (j & 3));
+      }
+      __stcs(reinterpret_cast<uint2*>(out) + i, make_uint2(o[0], o[1]));
+    }
+    done = nv << 3;
   }
+  for (int64_t p = done + tid; p < g.npix; p += nth) out[p] = slut[bin_of<DT>((unsigned)(uint16_t)src[p * g.sp])];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -337,7 +342,18 @@ scene_error_bip(SceneArgs g) {
       a.init();
       const T* xa = sa + (int64_t)threadIdx.x * B;
       const T* xr = sr + (int64_t)threadIdx.x * B;
-      for (int b = 0; b < B; ++b) a.template add<MODE>(ok ? abs((int)xa[b] - (int)xr[b]) : 0, g.kmax);
+      int b = 0;
+      if (sizeof(T) == 2 && (B & 1) == 0) {                   // two bands per shared-memory load, still in band order
+        constexpr int SDT = T(-1) < T(0) ? DM_I16 : DM_U16;
+        const uint32_t* wa = reinterpret_cast<const uint32_t*>(xa);
+        const uint32_t* wr = reinterpret_cast<const uint32_t*>(xr);
+        for (; b < B; b += 2) {
+          const uint32_t x = wa[b >> 1], y = wr[b >> 1];
+          a.template add<MODE>(ok ? abs(sample16<SDT>(x, 0) - sample16<SDT>(y, 0)) : 0, g.kmax);
+          a.template add<MODE>(ok ? abs(sample16<SDT>(x, 1) - sample16<SDT>(y, 1)) : 0, g.kmax);
+        }
+      }
+      for (; b < B; ++b) a.template add<MODE>(ok ? abs((int)xa[b] - (int)xr[b]) : 0, g.kmax);
       const float v = a.template finish<MODE>(B, g.kmax, g.thr);
       g.out[p] = v;
       vmax = __uint_as_float(max(__float_as_uint(vmax), __float_as_uint(v)));
@@ -434,13 +450,17 @@ diff1_scalar_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t band
 // a batched 2-D transpose [batch][R][C] -> [batch][C][R] through a padded shared-memory tile.
 template <typename T>
 __global__ void __launch_bounds__(256)
-transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t Cn, int64_t tiles_c, int64_t batch0) {
+transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int64_t Cn, int64_t tiles_fast, int r_fast,
+                 int64_t batch0) {
   __shared__ T tile[64][65];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
   const int64_t batch = batch0 + blockIdx.y;
   const T* s = src + batch * R * Cn;
   T* d = dst + batch * R * Cn;
-  const int64_t r0 = ((int64_t)blockIdx.x / tiles_c) * 64, c0 = ((int64_t)blockIdx.x % tiles_c) * 64;
+  // consecutive blocks walk the SHORT axis (the bands): the partial lines a tile leaves on the interleaved side
+  // are completed by its neighbours while they are still in L2
+  const int64_t t_slow = (int64_t)blockIdx.x / tiles_fast, t_fast = (int64_t)blockIdx.x % tiles_fast;
+  const int64_t r0 = (r_fast ? t_fast : t_slow) * 64, c0 = (r_fast ? t_slow : t_fast) * 64;
 #pragma unroll 4
   for (int j = 0; j < 64; j += 4) {
     const int64_t r = r0 + ty + j, c = c0 + tx;
@@ -451,6 +471,34 @@ transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t R, int6
   for (int j = 0; j < 64; j += 4) {
     const int64_t c = c0 + ty + j, r = r0 + tx;
     if (r < R && c < Cn) d[c * R + r] = tile[tx][ty + j];
+  }
+}
+
+// 16-bit elements, R and Cn even, 4-byte aligned cubes: global accesses are 32-bit words (two elements), so a
+// warp moves 128 contiguous bytes per instruction on both sides; the tile is kept as 16-bit elements with an
+// odd WORD pitch (66 elements = 33 words): row writes are conflict free, the column-pair reads two-way
+__global__ void __launch_bounds__(256)
+transpose16_pair_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t R, int64_t Cn, int64_t tiles_fast,
+                        int r_fast, int64_t batch0) {
+  __shared__ uint16_t tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 words x 8 rows
+  const int64_t batch = batch0 + blockIdx.y;
+  const uint32_t* s = src + batch * (R * Cn / 2);
+  uint32_t* d = dst + batch * (R * Cn / 2);
+  // consecutive blocks walk the SHORT axis (the bands): the partial lines a tile leaves on the interleaved side
+  // are completed by its neighbours while they are still in L2
+  const int64_t t_slow = (int64_t)blockIdx.x / tiles_fast, t_fast = (int64_t)blockIdx.x % tiles_fast;
+  const int64_t r0 = (r_fast ? t_fast : t_slow) * 64, c0 = (r_fast ? t_slow : t_fast) * 64;
+#pragma unroll
+  for (int j = 0; j < 64; j += 8) {
+    const int64_t r = r0 + ty + j, c = c0 + 2 * tx;
+    if (r < R && c < Cn) *reinterpret_cast<uint32_t*>(&tile[ty + j][2 * tx]) = __ldg(s + (r * Cn + c) / 2);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 64; j += 8) {
+    const int64_t c = c0 + ty + j, r = r0 + 2 * tx;
+    if (r < R && c < Cn) d[(c * R + r) / 2] = (uint32_t)tile[2 * tx][ty + j] | ((uint32_t)tile[2 * tx + 1][ty + j] << 16);
   }
 }
 
@@ -535,10 +583,17 @@ int launch_lut_bands(const dm_cube_t& c, const int32_t* sel, int nsel, const uin
     g.sel[i] = sel[i];
   }
   if (g.npix == 0) return DM_OK;
-  const dim3 grid((unsigned)grid_for((g.npix + 3) / 4, 256, 8), (unsigned)nsel);
-  if (c.dtype == DM_U8) lut_bands_kernel<uint8_t, DM_U8><<<grid, 256, 0, s>>>(g);
-  else if (c.dtype == DM_U16) lut_bands_kernel<uint16_t, DM_U16><<<grid, 256, 0, s>>>(g);
-  else lut_bands_kernel<uint16_t, DM_I16><<<grid, 256, 0, s>>>(g);
+  const dim3 grid((unsigned)grid_for((g.npix + 7) / 8, 512, 3), (unsigned)nsel);      // three 64 KB tables per SM
+  const size_t smem = 65536;
+#define DM_LUT(T, DT)                                                                                          \
+  do {                                                                                                         \
+    DM_CUDA(cudaFuncSetAttribute(lut_bands_kernel<T, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    lut_bands_kernel<T, DT><<<grid, 512, smem, s>>>(g);                                                        \
+  } while (0)
+  if (c.dtype == DM_U8) DM_LUT(uint8_t, DM_U8);
+  else if (c.dtype == DM_U16) DM_LUT(uint16_t, DM_U16);
+  else DM_LUT(uint16_t, DM_I16);
+#undef DM_LUT
   DM_LAUNCH_CHECK("lut_bands");
   return DM_OK;
 }
@@ -685,10 +740,16 @@ int launch_interleave(const void* src, void* dst, int eb, int from, int to, int6
   else { batch = rows; R = width; Cn = bands; }                               // BIP -> BIL
   const int64_t gx = (Cn + 63) / 64, gy = (R + 63) / 64;
   if (gx * gy > 0x7fffffffll) return fail(DM_EUNSUPPORTED, "dm_interleave: cube too large for one launch");
+  const int r_fast = R < Cn ? 1 : 0;
+  const int64_t tiles_fast = r_fast ? gy : gx;
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const dim3 grid((unsigned)(gx * gy), (unsigned)((batch - b0) < 65535 ? (batch - b0) : 65535));
-    if (eb == 1) transpose_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), R, Cn, gx, b0);
-    else transpose_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), R, Cn, gx, b0);
+    if (eb == 1)
+      transpose_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), R, Cn, tiles_fast, r_fast, b0);
+    else if (R % 2 == 0 && Cn % 2 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0)
+      transpose16_pair_kernel<<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst), R, Cn, tiles_fast, r_fast, b0);
+    else
+      transpose_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), R, Cn, tiles_fast, r_fast, b0);
     DM_LAUNCH_CHECK("transpose");
   }
   return DM_OK;

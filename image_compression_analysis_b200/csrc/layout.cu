@@ -1,31 +1,11 @@
-// Layout helper: (rows, width, bands) BIP -> (bands, rows, width) BSQ through a shared-memory tile,
-// so that both the read and the write side are coalesced.  Used by the host layer for the stencil
-// kernels (Sobel, Gaussian SSIM), which take BSQ, and for BIP cubes with an odd band count.
+// Layout helper dm_bip_to_bsq ((rows, width, bands) -> (bands, rows, width); the transpose itself lives in
+// adjacent.cu) and the multi-GPU combine of partial vectors.
 
 #include "dm_common.cuh"
 
 namespace dm {
 
 namespace {
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-bip_to_bsq_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t bands, int64_t npix) {
-  __shared__ T tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-  const int64_t p0 = (int64_t)blockIdx.x * 32, b0 = (int64_t)blockIdx.y * 32;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    const int64_t p = p0 + ty + j, b = b0 + tx;
-    if (p < npix && b < bands) tile[ty + j][tx] = src[p * bands + b];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    const int64_t b = b0 + ty + j, p = p0 + tx;
-    if (p < npix && b < bands) dst[b * npix + p] = tile[tx][ty + j];
-  }
-}
 
 // world gathered runs of `records` partial vectors -> one run (see dm_combine_partials in dm_b200.h)
 __global__ void __launch_bounds__(256)
@@ -72,15 +52,8 @@ int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands,
   if (elem_bytes != 1 && elem_bytes != 2) return fail(DM_EARG, "dm_bip_to_bsq: elem_bytes must be 1 or 2");
   const int64_t npix = rows * width;
   if (npix <= 0 || bands <= 0) return DM_OK;
-  const int64_t gx = (npix + 31) / 32, gy = (bands + 31) / 32;
-  if (gx > 0x7fffffffll || gy > 65535) return fail(DM_EUNSUPPORTED, "dm_bip_to_bsq: cube too large");
-  const dim3 grid((unsigned)gx, (unsigned)gy);
-  if (elem_bytes == 1)
-    bip_to_bsq_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), bands, npix);
-  else
-    bip_to_bsq_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t*>(src), static_cast<uint16_t*>(dst), bands, npix);
-  DM_LAUNCH_CHECK("bip_to_bsq");
-  return DM_OK;
+  // the batched 64x64 transpose of dm_interleave (32-bit accesses, tiles ordered along the band axis)
+  return launch_interleave(src, dst, elem_bytes, DM_BIP, DM_BSQ, bands, rows, width, s);
 }
 
 }  // namespace dm
