@@ -638,3 +638,32 @@ def test_error_max8_percentile_scaling(layout):
         got = ql.error_max8_arrays(ra, rb, None, 16, layout=layout)
         assert got["cap_g"] == want["cap_g"]
         assert np.array_equal(got["err8_g"], want["err8_g"]) and np.array_equal(got["err8_z"], want["err8_z"])
+
+
+def test_many_band_cube_read_through_rasterio_is_evaluated_as_bip():
+    """rasterio hands (B,H,W); a 180-band cube is transposed once on the device so that the three drop-in
+    calls take the BIP kernels (one-pass stats + SAM, register-resident SID, BIP Sobel).  Results vs oracle."""
+    from pathlib import Path
+    from oracle import distortion_oracle as orc, rasterio_stub
+    rasterio_stub.install()
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import ingest, quicklooks as ql
+    B, H, W, nd = 180, 21, 35, -32768
+    ref, dec = _rand_pair(61, "int16", B, H, W, 12)
+    ref[ref == nd] += 1; dec[dec == nd] += 1
+    bad = np.random.default_rng(62).random((H, W)) < 0.1
+    ref[:, bad] = nd; dec[:, bad] = nd
+    rasterio_stub.clear()
+    rasterio_stub.register("/mem/src.tif", ref, nodata=nd)
+    rasterio_stub.register("/mem/recon.tif", dec, nodata=nd)
+    pair, _ = ingest.load_pair("/mem/src.tif", "/mem/recon.tif")
+    assert pair.layout == "bip" and tuple(pair.ref.shape) == (H, W, B)
+    got = dm.compute_metrics(Path("/mem/src.tif"), Path("/mem/recon.tif"))
+    _check_metrics(got, orc.compute_metrics(ref, dec, None, extras=False, ref_nodata=nd, tst_nodata=nd))
+    spec = dm.compute_sam_sid_lmse_caseB(Path("/mem/src.tif"), Path("/mem/recon.tif"))
+    for k, w in orc.compute_sam_sid_lmse_caseB(ref, dec, None, ref_nodata=nd, tst_nodata=nd).items():
+        assert _close(spec[k], w), (k, spec[k], w)
+    og, oz = ql.write_error_max8("/mem/src.tif", "/mem/recon.tif", "/mem/out/recon", err_max_global=255, err_max_zoom=32)
+    o = orc.error_max8(ref, dec, 255, 32, ref_nodata=nd, tst_nodata=nd)
+    assert np.array_equal(rasterio_stub.fetch(og).data[0], o["err8_g"])
+    assert np.array_equal(rasterio_stub.fetch(oz).data[0], o["err8_z"])
