@@ -211,6 +211,15 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line.  Libraries write banners to file descriptor 1 behind Python's back
+    # (NCCL prints "NCCL version ..." there on this image), so descriptor 1 is pointed at stderr for the whole
+    # run and the JSON line goes to the saved original descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj) -> None:
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     import torch
     import torch.distributed as dist
@@ -223,8 +232,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.gpus != world and rank == 0:
         print(f"[bench] --gpus {args.gpus} but WORLD_SIZE={world}: reporting n_gpus={world}", file=sys.stderr)
@@ -405,7 +412,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(rows=512, reps=1)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
