@@ -230,6 +230,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    from image_compression_analysis_b200.engine import bind_host_to_gpu_numa
+    numa_node = None if os.environ.get("DM_NO_NUMA_BIND") else bind_host_to_gpu_numa(local)   # pinned staging local to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -364,7 +366,7 @@ def main():
                "h2d_bytes_per_step": PAIR_BYTES, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": ms_e2e / e2e_steps,
                "api": "engine.evaluate_host_pairs(pinned host cubes) [upload of pair i+1 overlaps the kernels, exchange, "
-                      "read-back and host finish of pair i] -> finish.*"}
+                      "read-back and host finish of pair i] -> finish.*", "host_numa_node": numa_node}
 
     if rank != 0:
         if world > 1:

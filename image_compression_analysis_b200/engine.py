@@ -80,6 +80,35 @@ def to_device(arr, device=None, non_blocking: bool = True) -> torch.Tensor:
     return t.to(device, non_blocking=non_blocking)
 
 
+def bind_host_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned staging buffers
+    allocated afterwards are local to the GPU's PCIe root (host-to-device copies of several ranks otherwise
+    cross the socket interconnect).  Returns the node, or None when the topology cannot be read or the
+    affinity cannot be set (containers with a restricted cpuset): best effort, never an error."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 _UPLOAD_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
