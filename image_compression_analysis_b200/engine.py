@@ -486,19 +486,20 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     want_planes = want.errmax or cap_g is not None or cap_z is not None
     use = plane if (plane is not None and metrics_mask) else None
     lut_g = lut_z = None
+    pl_e = pl_g = pl_z = None               # the planes THIS call writes (P may carry planes of an earlier call)
     ws = workspace(dev) if (want.sam or want.sid) else None
     if want_planes or want.sam or want.sid:
         if want.errmax:
-            P.planes["errmax"] = torch.empty(pair.npix, dtype=torch.int16, device=dev)
+            pl_e = P.planes["errmax"] = torch.empty(pair.npix, dtype=torch.int16, device=dev)
         if cap_g is not None:
             lut_g = _lut_on_device(cap_g, dev)
-            P.planes["err8_g"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+            pl_g = P.planes["err8_g"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
         if cap_z is not None:
             lut_z = _lut_on_device(cap_z, dev)
-            P.planes["err8_z"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
-    spectral_args = (_ptr(P.planes.get("errmax")),
-                     _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(P.planes.get("err8_g")), _ptr(P.hist8_g),
-                     _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(P.planes.get("err8_z")), _ptr(P.hist8_z))
+            pl_z = P.planes["err8_z"] = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+    spectral_args = (_ptr(pl_e),
+                     _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(pl_g), _ptr(P.hist8_g),
+                     _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(pl_z), _ptr(P.hist8_z))
     done_stats = done_spectral = False
     # one-pass BIP kernel: stats + error planes + SAM from a single read (the plane selects METRICS
     # pixels for the stats and QUICKLOOK / SPECTRAL pixels for the rest, so it needs use == plane)

@@ -178,3 +178,37 @@ def test_rate_sweep_is_monotonic_and_runs_in_one_run():
     assert np.all(np.isinf(psnr[13])) and np.all(sam[13] < 1e-5)              # last rate: lossless
     assert np.all(np.diff(psnr[:13].mean(1)) > 0) and np.all(np.diff(sam[:13].mean(1)) < 0)
     assert np.all(np.ptp(psnr[:13], axis=1) < 0.01) and np.all(np.ptp(sam[:13], axis=1) < 1e-3 * sam[:13].mean(1))
+
+
+def test_chained_launches_accumulate_exactly():
+    """Programmatic dependent launch lets launch N+1 start while launch N drains.  Fifty launches on the
+    Case-B cube accumulating into ONE partial vector (64-bit RED for the integers, the last block's ordered
+    `+=` for the SAM sums, the shared workspace counter) must equal fifty times the single result -- any race
+    between a draining launch and its successor would show here."""
+    import torch
+    from image_compression_analysis_b200.engine import DevicePair, Partials, PreparedFused, Want, evaluate
+    B, H, W = 180, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ref = torch.randint(0, 2500, (H, W, B), device="cuda", dtype=torch.int16, generator=g) * 4
+    tst = (ref + torch.randint(-3, 4, (H, W, B), device="cuda", dtype=torch.int16, generator=g)).clamp_(0, 32767)
+    pair = DevicePair(ref, tst, "uint16", "bip", B, H, W)
+    want = Want(stats=True, sam=True)
+    one = evaluate(pair, want).to_host()
+    n = 50
+    P = Partials.allocate(B, 0, ref.device, "uint16")
+    launch = PreparedFused(pair, want, P)
+    for _ in range(n):
+        launch.launch()
+    many = P.to_host()
+    assert np.array_equal(many.isum, n * one.isum)
+    assert np.array_equal(many.imax, one.imax)
+    acc = 0.0
+    for _ in range(n):
+        acc += float(one.spec[0])                       # the same left-to-right float64 additions
+    assert float(many.spec[0]) == acc and float(many.spec[2]) == n * float(one.spec[2])
+    # and interleaved with a launch that writes planes (no early trigger) and a masked one
+    P2 = Partials.allocate(B, 0, ref.device, "uint16")
+    for k in range(6):
+        evaluate(pair, Want(stats=True, sam=True, err8_caps=(255, 32) if k % 2 else (None, None)), out=P2)
+    h2 = P2.to_host()
+    assert np.array_equal(h2.isum[:B * 8], 6 * one.isum[:B * 8])
