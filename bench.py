@@ -249,8 +249,17 @@ def main():
     # all-gather + dm_combine_partials on a side stream: the exchange is latency bound)
     run, outs = Partials.allocate_run(args.warmup + args.steps, BANDS, 0, pairs[0].ref.device, "uint16")
 
-    from image_compression_analysis_b200.sharding import RunCombiner
-    combiner = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH) if world > 1 else None
+    from image_compression_analysis_b200.sharding import P2PRunCombiner, RunCombiner
+    combiner, exchange = None, "none"
+    if world > 1:
+        # DM_EXCHANGE=p2p: partial vectors pushed over NVLink peer memory instead of the NCCL all-gather
+        if os.environ.get("DM_EXCHANGE", "nccl") == "p2p":
+            try:
+                combiner, exchange = P2PRunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), "nvlink peer memory (dm_p2p_push / dm_p2p_combine)"
+            except Exception as e:      # noqa: BLE001  (IPC not available in this container, ...)
+                print(f"[bench] P2P exchange unavailable ({e}); using NCCL", file=sys.stderr)
+        if combiner is None:
+            combiner, exchange = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), "NCCL all-gather + dm_combine_partials"
 
     # the launches of the sweep are prepared once (all ctypes arguments built ahead): a step is one foreign call
     prepared = [PreparedFused(pairs[i % n_pairs], want, outs[i]) for i in range(args.warmup + args.steps)]
@@ -286,6 +295,8 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
+    if isinstance(combiner, P2PRunCombiner):
+        combiner.check_status()
     ms_local = ms_total                      # this rank's own timed region (the max over ranks is taken below)
     launches = L.dm_launch_count() - launches0
     clocks = sampler.stop()
@@ -393,7 +404,7 @@ def main():
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "layout": "bip", "bands": BANDS, "rows_per_gpu": ROWS, "width": WIDTH,
-                   "pair_bytes_per_gpu": PAIR_BYTES, "l2_policy": f"inputs larger than L2: {n_pairs} distinct 755 MB pairs rotated",
+                   "pair_bytes_per_gpu": PAIR_BYTES, "exchange": exchange, "l2_policy": f"inputs larger than L2: {n_pairs} distinct 755 MB pairs rotated",
                    "sharding": (f"row strips, one per GPU; the integer/float64 partials of every {COMBINE_BATCH} pairs are combined "
                                 "with one NCCL all-gather + dm_combine_partials on a side stream, overlapped with the next "
                                 "pairs' kernels; the timed region ends after the last combine") if world > 1 else "single GPU",

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -79,6 +79,13 @@ SYMBOLS = {
     "dm_scale_plane_u8": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, _P, _P]),
     "dm_diff1": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
     "dm_interleave": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "dm_p2p_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), _P]),
+    "dm_p2p_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "dm_p2p_close": (C.c_int, [_P]),
+    "dm_p2p_free": (C.c_int, [_P]),
+    "dm_p2p_push": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, _P]),
+    "dm_p2p_combine": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_int64, _P, _P, C.c_double, _P]),
 }
 
 _lib = None

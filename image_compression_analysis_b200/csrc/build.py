@@ -16,7 +16,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 PKG = HERE.parent
 ROOT = PKG.parent
-SOURCES = ["lib.cu", "stats.cu", "fused_bip.cu", "fused_bsq.cu", "validity.cu", "spectral.cu", "sobel.cu", "ssim.cu", "layout.cu", "adjacent.cu"]
+SOURCES = ["lib.cu", "stats.cu", "fused_bip.cu", "fused_bsq.cu", "validity.cu", "spectral.cu", "sobel.cu", "ssim.cu", "layout.cu", "adjacent.cu", "p2p.cu"]
 HEADERS = [HERE / "dm_common.cuh", ROOT / "include" / "dm_b200.h"]
 LIB = PKG / "libdm_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "dm_b200.h"
 
@@ -79,6 +80,16 @@ int launch_diff1(const void* src, void* dst, int dtype, int arith, int inverse, 
                  int64_t band_stride, cudaStream_t s);
 int launch_interleave(const void* src, void* dst, int eb, int from, int to, int64_t bands, int64_t rows, int64_t width,
                       cudaStream_t s);
+
+int p2p_alloc(int64_t bytes, void** ptr, void* handle64);
+int p2p_open(const void* handle64, void** ptr);
+int p2p_close(void* ptr);
+int p2p_free(void* ptr);
+int launch_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int world,
+                    uint64_t flag_value, cudaStream_t s);
+int launch_p2p_combine(const void* gathered, const void* flags, int world, uint64_t need, int64_t capacity, int64_t rec0,
+                       int64_t nrec, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out, uint32_t* status,
+                       double timeout_s, cudaStream_t s);
 
 // ---- device side ------------------------------------------------------------------------------
 #ifdef __CUDACC__

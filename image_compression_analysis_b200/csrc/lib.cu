@@ -155,4 +155,21 @@ int dm_interleave(const void* src, void* dst, int32_t elem_bytes, int32_t from_l
   return launch_interleave(src, dst, elem_bytes, from_layout, to_layout, bands, rows, width, static_cast<cudaStream_t>(stream));
 }
 
+int dm_p2p_alloc(int64_t bytes, void** ptr, void* handle64) { return p2p_alloc(bytes, ptr, handle64); }
+int dm_p2p_open(const void* handle64, void** ptr) { return p2p_open(handle64, ptr); }
+int dm_p2p_close(void* ptr) { return p2p_close(ptr); }
+int dm_p2p_free(void* ptr) { return p2p_free(ptr); }
+
+int dm_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int32_t world,
+                uint64_t flag_value, void* stream) {
+  return launch_p2p_push(src, total_words, peer_dst, peer_flag, world, flag_value, static_cast<cudaStream_t>(stream));
+}
+
+int dm_p2p_combine(const void* gathered, const void* flags, int32_t world, uint64_t need, int64_t capacity, int64_t rec0,
+                   int64_t nrec, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out, uint32_t* status, double timeout_s,
+                   void* stream) {
+  return launch_p2p_combine(gathered, flags, world, need, capacity, rec0, nrec, n_sum, n_max, n_f64, out, status, timeout_s,
+                            static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

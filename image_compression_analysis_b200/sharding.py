@@ -176,3 +176,95 @@ class RunCombiner:
         import torch
         self._flush(upto)
         torch.cuda.current_stream().wait_stream(self.stream)
+
+
+class P2PRunCombiner:
+    """RunCombiner without a collective library: the partial vectors of a sweep are PUSHED over NVLink into the
+    exchange buffer every peer keeps (libdm_b200's dm_p2p_*: cudaMalloc + CUDA IPC, one small kernel with a CTA
+    per destination, system-scope release/acquire flags), and each rank reduces its local copy in rank order.
+    Same interface and same results as RunCombiner (bit-identical: the reduction order is the same).
+
+    Set-up needs `torch.distributed` only to hand the 64-byte IPC handles around.  Anything that fails here
+    raises, and the caller falls back to RunCombiner (NCCL)."""
+
+    def __init__(self, run, bands: int, hist_bins: int = 0, batch: int = 8, group=None, timeout_s: float = 20.0):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, lib
+        from .engine import Partials
+        self.run, self.bands, self.hist_bins, self.batch, self.group = run, bands, hist_bins, max(1, batch), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.capacity, self.words = int(run.shape[0]), int(run.shape[1])
+        self.sizes = Partials.sizes(bands, hist_bins)
+        assert sum(self.sizes) == self.words
+        self.timeout_s = timeout_s
+        self.stream = torch.cuda.Stream()
+        self._next = 0
+        self._L = lib()
+        data_bytes = self.world * self.capacity * self.words * 8
+        self._flags_off = (data_bytes + 255) // 256 * 256
+        total = self._flags_off + 256
+        base, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        check(self._L.dm_p2p_alloc(total, C.byref(base), handle))
+        self._base = base.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._peers = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self._peers.append(self._base)
+                continue
+            p = C.c_void_p()
+            check(self._L.dm_p2p_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+            self._peers.append(p.value)
+        self._status = torch.zeros(1, dtype=torch.int32, device=run.device)
+        dist.barrier(group=group)           # every buffer exists and is mapped before anybody pushes
+
+    def done(self, i: int) -> None:
+        if i + 1 - self._next >= self.batch:
+            self._flush(i + 1)
+
+    def _flush(self, upto: int) -> None:
+        import ctypes as C
+        import torch
+        from ._lib import check
+        if upto <= self._next:
+            return
+        i0, n = self._next, upto - self._next
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            st = C.c_void_p(self.stream.cuda_stream)
+            slot = (self.rank * self.capacity + i0) * self.words * 8
+            dst = (C.c_void_p * self.world)(*[p + slot for p in self._peers])
+            flg = (C.c_void_p * self.world)(*[p + self._flags_off + 8 * self.rank for p in self._peers])
+            src = self.run.data_ptr() + i0 * self.words * 8
+            check(self._L.dm_p2p_push(C.c_void_p(src), n * self.words, dst, flg, self.world, upto, st))
+            ni, nm, nf = self.sizes
+            check(self._L.dm_p2p_combine(C.c_void_p(self._base), C.c_void_p(self._base + self._flags_off), self.world, upto,
+                                         self.capacity, i0, n, ni, nm, nf, C.c_void_p(src), C.c_void_p(self._status.data_ptr()),
+                                         float(self.timeout_s), st))
+        self._next = upto
+
+    def finish(self, upto: int) -> None:
+        import torch
+        self._flush(upto)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def check_status(self) -> None:
+        """Raises if a combine gave up waiting for a peer (call after a synchronisation point)."""
+        if int(self._status.item()) != 0:
+            raise RuntimeError("P2P exchange: a peer's partial vectors did not arrive within the time-out")
+
+    def close(self) -> None:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)      # nobody still reads or writes a buffer that is about to go away
+        for r, p in enumerate(self._peers):
+            if r != self.rank:
+                self._L.dm_p2p_close(p)
+        self._L.dm_p2p_free(self._base)
+        self._peers = []

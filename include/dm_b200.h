@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 4
+#define DM_ABI_VERSION 5
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -264,6 +264,26 @@ int dm_diff1(const void* src, void* dst, int32_t dtype, int32_t arith, int32_t i
  * contiguous cubes of 1- or 2-byte samples. */
 int dm_interleave(const void* src, void* dst, int32_t elem_bytes, int32_t from_layout, int32_t to_layout,
                   int64_t bands, int64_t rows, int64_t width, void* stream);
+
+/* ===== NVLink peer-memory exchange of partial vectors (alternative to the NCCL all-gather) =====
+ * Every rank owns one exchange buffer  [world][capacity] partial vectors | world uint64 arrival flags,
+ * allocated by dm_p2p_alloc (cudaMalloc, zeroed) and exported as a 64-byte CUDA IPC handle that the host
+ * layer hands to the other ranks (any transport; torch.distributed.all_gather_object here); dm_p2p_open maps a
+ * peer's buffer.  dm_p2p_push copies `total_words` 8-byte words from src into peer_dst[r] for every r (one
+ * CTA per destination, plain stores over NVLink; r = own rank is a local copy) and then stores flag_value to
+ * peer_flag[r] with system-scope release.  dm_p2p_combine waits (system-scope acquire, at most timeout_s,
+ * then *status = 1 and nothing is written) until all `world` LOCAL flags are >= need and reduces records
+ * [rec0, rec0+nrec) of the world local copies into out exactly as dm_combine_partials does.
+ * peer_dst / peer_flag are HOST arrays of `world` device pointers. */
+int dm_p2p_alloc(int64_t bytes, void** ptr, void* handle64);
+int dm_p2p_open(const void* handle64, void** ptr);
+int dm_p2p_close(void* ptr);
+int dm_p2p_free(void* ptr);
+int dm_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int32_t world,
+                uint64_t flag_value, void* stream);
+int dm_p2p_combine(const void* gathered, const void* flags, int32_t world, uint64_t need, int64_t capacity,
+                   int64_t rec0, int64_t nrec, int64_t n_sum, int64_t n_max, int64_t n_f64, void* out,
+                   uint32_t* status, double timeout_s, void* stream);
 
 #ifdef __cplusplus
 }

@@ -667,3 +667,18 @@ def test_many_band_cube_read_through_rasterio_is_evaluated_as_bip():
     o = orc.error_max8(ref, dec, 255, 32, ref_nodata=nd, tst_nodata=nd)
     assert np.array_equal(rasterio_stub.fetch(og).data[0], o["err8_g"])
     assert np.array_equal(rasterio_stub.fetch(oz).data[0], o["err8_z"])
+
+
+def test_p2p_exchange_matches_nccl_on_two_gpus():
+    """NVLink peer-memory exchange (dm_p2p_push / dm_p2p_combine) == NCCL all-gather + dm_combine_partials, bit
+    for bit, on every rank.  Needs two GPUs: skipped on a one-GPU box (run with `gpurun --gpus 2`)."""
+    import subprocess, sys, torch
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", str(root / "tools" / "check_p2p.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("p2p == nccl: True; same on all ranks: True") == 2
