@@ -251,15 +251,24 @@ def main():
 
     from image_compression_analysis_b200.sharding import P2PRunCombiner, RunCombiner
     combiner, exchange = None, "none"
+    NCCL_EXCHANGE = "NCCL all-gather + dm_combine_partials"
     if world > 1:
-        # DM_EXCHANGE=p2p: partial vectors pushed over NVLink peer memory instead of the NCCL all-gather
-        if os.environ.get("DM_EXCHANGE", "nccl") == "p2p":
+        # Default: partial vectors pushed over NVLink peer memory (no collective library in the loop).  It is
+        # proven during the warm-up below and replaced by the NCCL exchange -- on ALL ranks together -- if the
+        # IPC set-up fails or a peer's data does not arrive.  DM_EXCHANGE=nccl forces the NCCL path.
+        ok = 0
+        if os.environ.get("DM_EXCHANGE", "p2p") == "p2p":
             try:
-                combiner, exchange = P2PRunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), "nvlink peer memory (dm_p2p_push / dm_p2p_combine)"
+                combiner = P2PRunCombiner(run, BANDS, 0, batch=COMBINE_BATCH, timeout_s=10.0)
+                ok = 1
             except Exception as e:      # noqa: BLE001  (IPC not available in this container, ...)
-                print(f"[bench] P2P exchange unavailable ({e}); using NCCL", file=sys.stderr)
-        if combiner is None:
-            combiner, exchange = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), "NCCL all-gather + dm_combine_partials"
+                print(f"[bench] rank {rank}: P2P exchange unavailable ({e})", file=sys.stderr)
+        t_ok = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 1:
+            exchange = "nvlink peer memory (dm_p2p_push / dm_p2p_combine)"
+        else:
+            combiner, exchange = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), NCCL_EXCHANGE
 
     # the launches of the sweep are prepared once (all ctypes arguments built ahead): a step is one foreign call
     prepared = [PreparedFused(pairs[i % n_pairs], want, outs[i]) for i in range(args.warmup + args.steps)]
@@ -281,6 +290,22 @@ def main():
     if combiner is not None:
         combiner.finish(args.warmup)
     barrier()
+    if isinstance(combiner, P2PRunCombiner):
+        # the warm-up pushed and combined real records: did every peer's data arrive, on every rank?
+        bad = 0
+        try:
+            combiner.check_status()
+        except RuntimeError as e:
+            print(f"[bench] rank {rank}: {e}", file=sys.stderr)
+            bad = 1
+        if os.environ.get("DM_EXCHANGE_FORCE_FALLBACK"):      # exercises the switch below (tests)
+            bad = 1
+        t_bad = torch.tensor([bad], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t_bad, op=dist.ReduceOp.MAX)
+        if int(t_bad.item()):
+            combiner, exchange = RunCombiner(run, BANDS, 0, batch=COMBINE_BATCH), NCCL_EXCHANGE
+            combiner._next = args.warmup            # the warm-up records are not part of the result
+        barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                       # one sampling thread per box is enough (and NVML serialises)

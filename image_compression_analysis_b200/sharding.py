@@ -199,25 +199,50 @@ class P2PRunCombiner:
         self.sizes = Partials.sizes(bands, hist_bins)
         assert sum(self.sizes) == self.words
         self.timeout_s = timeout_s
-        self.stream = torch.cuda.Stream()
         self._next = 0
         self._L = lib()
+        first_error = None
         data_bytes = self.world * self.capacity * self.words * 8
         self._flags_off = (data_bytes + 255) // 256 * 256
         total = self._flags_off + 256
+        # Set-up is collective and must FAIL collectively: a rank that cannot allocate or map still takes part
+        # in the two object gathers, and everybody raises together (the caller then falls back to NCCL).
         base, handle = C.c_void_p(), (C.c_ubyte * 64)()
-        check(self._L.dm_p2p_alloc(total, C.byref(base), handle))
+        mine = None
+        try:
+            check(self._L.dm_p2p_alloc(total, C.byref(base), handle))
+            mine = bytes(handle)
+        except Exception as e:          # noqa: BLE001
+            first_error = e
         self._base = base.value
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        self._peers = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self._peers.append(self._base)
-                continue
-            p = C.c_void_p()
-            check(self._L.dm_p2p_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
-            self._peers.append(p.value)
+        dist.all_gather_object(handles, mine, group=group)
+        self._peers, opened = [], True
+        if all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self._peers.append(self._base)
+                        continue
+                    p = C.c_void_p()
+                    check(self._L.dm_p2p_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+                    self._peers.append(p.value)
+            except Exception as e:      # noqa: BLE001
+                first_error, opened = e, False
+        else:
+            opened = False
+        oks = [None] * self.world
+        dist.all_gather_object(oks, opened, group=group)
+        if not all(oks):
+            for r, p in enumerate(self._peers):
+                if r != self.rank:
+                    self._L.dm_p2p_close(p)
+            if self._base:
+                self._L.dm_p2p_free(self._base)
+            self._peers = []
+            raise RuntimeError(f"P2P exchange set-up failed on rank(s) {[r for r, o in enumerate(oks) if not o]}"
+                               + (f": {first_error}" if first_error is not None else ""))
+        self.stream = torch.cuda.Stream()
         self._status = torch.zeros(1, dtype=torch.int32, device=run.device)
         dist.barrier(group=group)           # every buffer exists and is mapped before anybody pushes
 

@@ -186,3 +186,37 @@ def test_gloo_world2_combine_equals_single_shot(built_lib, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2, r.stdout + r.stderr
+
+
+_P2P_FAIL_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["DM_ROOT"])
+import torch, torch.distributed as dist
+dist.init_process_group("gloo")
+from image_compression_analysis_b200.engine import Partials
+from image_compression_analysis_b200.sharding import P2PRunCombiner
+run, _ = Partials.allocate_run(4, 6, 0, torch.device("cpu"), "uint16")
+try:
+    P2PRunCombiner(run, 6, 0, batch=2)
+    print("unexpected success")
+except RuntimeError as e:
+    print("raised together:", str(e)[:60])
+dist.barrier()
+print("ok")
+'''
+
+
+def test_p2p_exchange_setup_fails_collectively(built_lib, tmp_path):
+    """Without a usable GPU the peer-memory set-up cannot allocate: every rank must leave the constructor with
+    the same RuntimeError (no rank left waiting in a collective), so that the caller can fall back to NCCL."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the set-up would succeed")
+    script = tmp_path / "worker_p2p.py"
+    script.write_text(_P2P_FAIL_WORKER)
+    env = dict(os.environ, DM_ROOT=str(ROOT), MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29519", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("raised together") == 2 and r.stdout.count("ok") == 2, r.stdout + r.stderr
