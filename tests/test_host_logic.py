@@ -220,3 +220,12 @@ def test_p2p_exchange_setup_fails_collectively(built_lib, tmp_path):
                        capture_output=True, text=True, env=env, timeout=300, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("raised together") == 2 and r.stdout.count("ok") == 2, r.stdout + r.stderr
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/dm_b200.h must compile as C99 (and as C++) on its own."""
+    hdr = str(ROOT / "include" / "dm_b200.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
