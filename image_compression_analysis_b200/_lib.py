@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -58,6 +58,7 @@ SYMBOLS = {
     "dm_last_error": (C.c_char_p, []),
     "dm_device_sm_count": (C.c_int, []),
     "dm_launch_count": (C.c_int64, []),
+    "dm_launch_chaining": (None, [C.c_int32]),
     "dm_validity": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P]),
     "dm_fused_stats": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
     "dm_workspace_bytes": (C.c_int64, []),

@@ -14,6 +14,7 @@ int fail(int code, const char* fmt, ...);           // records dm_last_error(), 
 int cuda_fail(cudaError_t e, const char* what);     // DM_ECUDA with the CUDA error text
 int sm_count();                                     // SMs of the current device (cached), <0 on error
 void count_launch();                                // one more kernel launched (dm_launch_count)
+bool launch_chaining();                             // dm_launch_chaining() state of this thread
 
 #define DM_CUDA(expr)                                              \
   do {                                                             \

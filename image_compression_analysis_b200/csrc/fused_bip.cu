@@ -645,12 +645,13 @@ fused_ct_kernel(FusedArgs g) {
   if (tid == 0) {
     for (int it = 0; it < kStages; ++it) issue_tile(it);
   }
-  // Programmatic dependent launch: a following launch of this kernel (run_ct sets the attribute) may
-  // start its CTAs as ours exit, instead of after the whole grid -- the tail of this launch (CTAs with
-  // one tile fewer, the last block's ordered reduction) then overlaps the next pair's first tiles.  The
-  // next launch only READS the cubes before its own griddepcontrol.wait (below, ahead of every global
-  // write), so nothing it does early can race with what is still running here.  Variants that write
-  // per-pixel planes do not trigger early: two launches may be given the same planes.
+  // Programmatic dependent launch: a following launch of this kernel (run_ct sets the attribute while the
+  // caller has launch chaining on) may start its CTAs as ours exit, instead of after the whole grid -- the
+  // tail of this launch (CTAs with one tile fewer, the last block's ordered reduction) then overlaps the
+  // next pair's first tiles.  The next launch only READS the cubes before its own griddepcontrol.wait
+  // (below, ahead of every global write), so nothing it does early can race with what is still running
+  // here.  Variants that write per-pixel planes do not trigger early: two launches may be given the same
+  // planes.
   if (!ERR) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < G::BAND_WARPS) {
@@ -1122,7 +1123,10 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
   if (sms < 0) return DM_ECUDA;
   int64_t grid = sms < kMaxPartialBlocks ? sms : kMaxPartialBlocks;
   if (grid > g.ntiles) grid = g.ntiles;
-  static const bool pdl = []() { const char* e = getenv("DM_NO_PDL"); return !(e && atoi(e)); }();
+  // programmatic dependent launch only while the caller has switched launch chaining on (dm_launch_chaining):
+  // a chained launch reads its inputs before the preceding kernel's writes are guaranteed to be flushed
+  static const bool pdl_allowed = []() { const char* e = getenv("DM_NO_PDL"); return !(e && atoi(e)); }();
+  const bool pdl = pdl_allowed && launch_chaining();
 #define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
   do {                                                                                                \
     auto k = fused_ct_kernel<BANDS, DT, MASK, ERR, MPW>;                                              \

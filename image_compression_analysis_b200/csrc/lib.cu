@@ -12,6 +12,10 @@ static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static thread_local bool g_chaining = false;
+bool launch_chaining() { return g_chaining; }
+void set_launch_chaining(bool on) { g_chaining = on; }
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -23,6 +27,8 @@ int fail(int code, const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   return fail(DM_ECUDA, "CUDA error in %s: %s", what, cudaGetErrorString(e));
 }
+
+void set_launch_chaining(bool on);
 
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -46,6 +52,7 @@ using namespace dm;
 extern "C" {
 
 int dm_abi_version(void) { return DM_ABI_VERSION; }
+void dm_launch_chaining(int32_t on) { dm::set_launch_chaining(on != 0); }
 const char* dm_last_error(void) { return g_err; }
 int dm_device_sm_count(void) { return sm_count(); }
 int64_t dm_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }

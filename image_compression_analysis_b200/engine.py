@@ -450,13 +450,25 @@ class PreparedFused:
         self._keep = (pair, out, plane, workspace(pair.ref.device) if want.sam else None)
         self._cp = pair.c_pair()
         self._fn = lib().dm_fused_bip
+        self._chain = lib().dm_launch_chaining
         ws = self._keep[3]
         self._args = (C.byref(self._cp), _ptr(plane), _ptr(out.sums), _ptr(out.imax), None, None, 0, None, None,
                       None, 0, None, None, 1 if want.sam else 0, _ptr(out.spec), _ptr(ws), _stream_ptr())
         out.used_mask = plane is not None
 
-    def launch(self) -> None:
-        check(self._fn(*self._args))
+    def launch(self, chain: bool = True) -> None:
+        """chain=True: this launch may start while the previous kernel on the stream drains (programmatic
+        dependent launch; see dm_launch_chaining in include/dm_b200.h).  The cubes of the pair must not be the
+        output of the kernel issued immediately before this launch on the same stream -- true for a sweep over
+        resident cubes, which is what this class is for; pass chain=False otherwise."""
+        if chain:
+            self._chain(1)
+            try:
+                check(self._fn(*self._args))
+            finally:
+                self._chain(0)
+        else:
+            check(self._fn(*self._args))
 
 
 def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 5
+#define DM_ABI_VERSION 6
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -148,6 +148,14 @@ int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
  * 16-bit samples, bands a multiple of 4 in 4..256, 16-byte aligned cubes; anything else returns
  * DM_EUNSUPPORTED and the caller uses the two separate passes.  180-band cubes (EnMAP) take a kernel
  * specialised at compile time for that pixel pitch; a partial last tile goes through the generic one. */
+/* Launch chaining for sweeps (thread-local switch, default OFF).  While it is on, launches of the 180-band
+ * one-pass kernel carry the programmatic-stream-serialization attribute: the next launch's CTAs start as the
+ * previous launch's CTAs exit, so that tail and ramp-up overlap (0.79 -> 0.85 of the HBM peak in a sweep).  A
+ * chained launch READS its cubes (and validity plane) before the preceding kernel in the stream is guaranteed to
+ * have flushed its writes -- every global WRITE of the launch waits (griddepcontrol.wait) -- so switch it on only
+ * when the inputs of a launch are not produced by the kernel issued immediately before it on the same stream
+ * (a sweep over cubes that are already resident: engine.PreparedFused). */
+void dm_launch_chaining(int32_t on);
 int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
                  uint16_t* errmax_out,
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,

@@ -22,7 +22,7 @@ def built_lib():
 
 def test_library_exports_every_declared_symbol(built_lib):
     header = (ROOT / "include" / "dm_b200.h").read_text()
-    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(dm_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|int64_t|void|const char\*)\s+(dm_\w+)\s*\(", header, flags=re.M))
     assert declared, "no declarations parsed from include/dm_b200.h"
     assert declared == set(built_lib.SYMBOLS), (declared ^ set(built_lib.SYMBOLS))
     lib = built_lib.lib()               # binds every symbol, raises if one is missing
