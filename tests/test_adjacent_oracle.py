@@ -130,3 +130,32 @@ def test_oracle_vs_live_reference_random():
         if B > 1:
             assert np.array_equal(adj.diff1_forward(s[1], s[0], "int16"), jw._diff1_forward(s[1], s[0], "int16"))
             assert np.array_equal(adj.diff1_inverse(s[1], s[0], "int16"), jw._diff1_inverse(s[1], s[0], "int16"))
+
+
+def test_scene_error_oracle_vs_live_reference_random(tmp_path):
+    """make_scene_error_map of the mounted reference on fresh random cubes, all modes and both scales."""
+    from oracle import rasterio_stub, reference_loader as rl
+    if not rl.available():
+        pytest.skip("reference tree not mounted")
+    from PIL import Image
+    mb = rl.make_baseline_B()
+    rng = np.random.default_rng(91)
+    for trial, (dt, kb) in enumerate((("uint16", 2), ("int16", 3), ("uint8", 1))):
+        info = np.iinfo(dt)
+        B, H, W = int(rng.integers(1, 7)), int(rng.integers(3, 30)), int(rng.integers(3, 30))
+        ref = rng.integers(max(info.min, -3000), min(info.max, 3000) + 1, (B, H, W)).astype(dt)
+        cmp_ = np.clip(ref.astype(np.int64) + rng.integers(-(1 << kb), (1 << kb) + 1, ref.shape), info.min, info.max).astype(dt)
+        mask = rng.random((H, W)) > 0.2
+        rasterio_stub.clear()
+        rasterio_stub.register("/mem/r.tif", ref)
+        rasterio_stub.register("/mem/c.tif", cmp_)
+        mp = tmp_path / f"m{trial}.tif"
+        mp.write_bytes(b"x")
+        rasterio_stub.register(mp, mask.astype(np.uint8))
+        for mode in ("mean", "rms", "count3", "max", "p95"):
+            for scale in ("fixed", "auto"):
+                png = tmp_path / f"{trial}_{mode}_{scale}.png"
+                mb.make_scene_error_map("/mem/r.tif", "/mem/c.tif", mp, scale, kb, png, err_mode=mode)
+                want = np.array(Image.open(png))
+                got, _ = adj.scene_error_map(ref, cmp_, mask, scale, kb, mode)
+                assert np.array_equal(got, want), (dt, mode, scale)
