@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -67,6 +67,7 @@ SYMBOLS = {
     "dm_fused_bip": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                C.c_int32, _P, _P, _P]),
     "dm_fused_bsq": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "dm_sobel_mag": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "dm_sobel_nblocks": (C.c_int, []),
     "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_ssim_nblocks": (C.c_int, []),

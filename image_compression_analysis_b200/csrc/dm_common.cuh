@@ -58,6 +58,7 @@ int64_t launch_validity_ct(const dm_pair_t& p, const uint8_t* valid_in, uint8_t*
 int launch_fused_bsq(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
                      const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z,
                      int cap_z, uint8_t* err8_z, int64_t* hist8_z, cudaStream_t s);
+int launch_sobel_mag(const void* img, int dtype, int64_t rows, int64_t width, double* out, cudaStream_t s);
 int sobel_nblocks();
 int ssim_nblocks();
 int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0,

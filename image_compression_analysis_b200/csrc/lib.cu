@@ -98,6 +98,10 @@ int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
                           hist8_z, static_cast<cudaStream_t>(stream));
 }
 
+int dm_sobel_mag(const void* img, int32_t dtype, int64_t rows, int64_t width, double* out, void* stream) {
+  return launch_sobel_mag(img, dtype, rows, width, out, static_cast<cudaStream_t>(stream));
+}
+
 int dm_sobel_nblocks(void) { return sobel_nblocks(); }
 
 int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,

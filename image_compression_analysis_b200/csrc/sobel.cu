@@ -211,7 +211,49 @@ sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restri
   }
 }
 
+// ---- magnitude map (the reference's sobel_mag as a function of its own, run_codec.py:123-137) -----------
+// thread per pixel, neighbours through L1 / L2 (an (H,W) plane is read ~once from HBM), edge replication by
+// index clamping, exact integer gradients, correctly rounded square root: bit-identical to the reference.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sobel_mag_kernel(const T* __restrict__ img, int64_t rows, int64_t width, double* __restrict__ out) {
+  const int64_t n = rows * width;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t y = i / width, x = i - y * width;
+    const int64_t y0 = y > 0 ? y - 1 : 0, y2 = y + 1 < rows ? y + 1 : rows - 1;
+    const int64_t x0 = x > 0 ? x - 1 : 0, x2 = x + 1 < width ? x + 1 : width - 1;
+    const T* r0 = img + y0 * width;
+    const T* r1 = img + y * width;
+    const T* r2 = img + y2 * width;
+    const int p00 = (int)__ldg(r0 + x0), p01 = (int)__ldg(r0 + x), p02 = (int)__ldg(r0 + x2);
+    const int p10 = (int)__ldg(r1 + x0), p12 = (int)__ldg(r1 + x2);
+    const int p20 = (int)__ldg(r2 + x0), p21 = (int)__ldg(r2 + x), p22 = (int)__ldg(r2 + x2);
+    const int gx = (p00 - p02) + 2 * (p10 - p12) + (p20 - p22);
+    const int gy = (p00 - p20) + 2 * (p01 - p21) + (p02 - p22);
+    const double fx = (double)gx, fy = (double)gy;
+    out[i] = __dsqrt_rn(fma(fx, fx, fy * fy));
+  }
+}
+
 }  // namespace
+
+int launch_sobel_mag(const void* img, int dtype, int64_t rows, int64_t width, double* out, cudaStream_t s) {
+  if (!img || !out) return fail(DM_EARG, "dm_sobel_mag: null pointer");
+  if (rows < 0 || width < 0) return fail(DM_EARG, "dm_sobel_mag: bad geometry");
+  if (rows * width == 0) return DM_OK;
+  const int sms = sm_count();
+  if (sms < 0) return DM_ECUDA;
+  int64_t grid = (rows * width + 255) / 256;
+  if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
+  switch (dtype) {
+    case DM_U8: sobel_mag_kernel<uint8_t><<<(unsigned)grid, 256, 0, s>>>(static_cast<const uint8_t*>(img), rows, width, out); break;
+    case DM_U16: sobel_mag_kernel<uint16_t><<<(unsigned)grid, 256, 0, s>>>(static_cast<const uint16_t*>(img), rows, width, out); break;
+    case DM_I16: sobel_mag_kernel<int16_t><<<(unsigned)grid, 256, 0, s>>>(static_cast<const int16_t*>(img), rows, width, out); break;
+    default: return fail(DM_EARG, "dm_sobel_mag: bad dtype");
+  }
+  DM_LAUNCH_CHECK("sobel_mag");
+  return DM_OK;
+}
 
 int sobel_nblocks() { return kSobBlocks; }
 

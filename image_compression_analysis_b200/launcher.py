@@ -23,6 +23,7 @@ def bind(run_codec_module) -> None:
     run_codec_module.mse = dm.mse
     run_codec_module.psnr = dm.psnr
     run_codec_module.ssim_global = dm.ssim_global
+    run_codec_module.sobel_mag = dm.sobel_mag
 
 
 def main(argv=None) -> int:

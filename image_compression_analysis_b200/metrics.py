@@ -195,6 +195,23 @@ def compute_sam_sid_lmse_caseB(ref_path: Path, tst_path: Path, valid: Optional[n
     return compute_sam_sid_lmse_caseB_pair(pair, m)
 
 
+def sobel_mag(img: np.ndarray) -> np.ndarray:
+    """3x3 Sobel gradient magnitude of one (H,W) band as float64 (run_codec.py:123-137), on the GPU.
+    Integer samples of up to 16 bits (what the path sees); other sample types are an error, not a CPU detour."""
+    import ctypes as C
+    from ._lib import check, lib
+    from .engine import _ptr, _stream_ptr
+    img = np.asarray(img)
+    if img.ndim != 2:
+        raise ValueError("sobel_mag takes one (H,W) band")
+    code = dtype_code(img.dtype)
+    H, W = img.shape
+    dev_img = to_device(img)
+    out = torch.empty((H, W), dtype=torch.float64, device=dev_img.device)
+    check(lib().dm_sobel_mag(_ptr(dev_img), code, H, W, _ptr(out), _stream_ptr()))
+    return out.cpu().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # additions: Gaussian-window SSIM, everything-at-once
 # ---------------------------------------------------------------------------------------------

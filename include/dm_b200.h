@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 6
+#define DM_ABI_VERSION 7
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -178,6 +178,9 @@ int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
  * Counts buffer rows [row_begin,row_end); buffer row 0 is image row img_row0 of img_rows, and the
  * buffer must hold one halo row on each side that is not an image border.
  * out: double[bands * dm_sobel_nblocks()] per-(band,block) partials (written, not accumulated). */
+/* sobel_mag as a function of its own (run_codec.py:123-137): float64 magnitude map of one (rows, width) plane,
+ * 3x3 Sobel pair with edge replication; bit-identical to the reference for 8/16-bit integer samples. */
+int dm_sobel_mag(const void* img, int32_t dtype, int64_t rows, int64_t width, double* out, void* stream);
 int dm_sobel_nblocks(void);
 int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,
                   int64_t img_rows, double* out, void* stream);

@@ -682,3 +682,21 @@ def test_p2p_exchange_matches_nccl_on_two_gpus():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("p2p == nccl: True; same on all ranks: True") == 2
+
+
+@pytest.mark.parametrize("dtype", ["uint16", "int16", "uint8"])
+def test_sobel_mag_map_is_bit_identical(dtype):
+    """sobel_mag(img) as a drop-in of its own (run_codec.py:123-137): exact integer gradients and a correctly
+    rounded square root, so the float64 map equals the reference's bit for bit (odd sizes, 1-pixel-wide image)."""
+    import image_compression_analysis_b200 as dm
+    from oracle import distortion_oracle as orc
+    info = np.iinfo(dtype)
+    rng = np.random.default_rng(3)
+    for H, W in ((37, 53), (1, 9), (8, 1), (64, 64)):
+        img = rng.integers(info.min, info.max + 1, (H, W)).astype(dtype)
+        got = dm.sobel_mag(img)
+        want = orc.sobel_mag(img)
+        assert got.dtype == np.float64 and got.shape == (H, W)
+        assert np.array_equal(got.view(np.int64), want.view(np.int64)), (dtype, H, W)
+    with pytest.raises(TypeError):
+        dm.sobel_mag(np.zeros((4, 4), np.float32))
