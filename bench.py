@@ -449,7 +449,7 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(rows=512, reps=1)
+        line["cpu_baseline"] = cpu_baseline_single(rows=512, reps=3)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
