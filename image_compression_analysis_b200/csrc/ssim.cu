@@ -19,6 +19,8 @@
 //           shared-memory loads feed 77 DFMA (2.4 loads per output and plane instead of 11), then the
 //           SSIM formula; block-ordered partial sums
 // Column index is the fastest thread index in both passes, so shared-memory accesses are conflict free.
+// (Tried: 38-row tiles with 192 threads and 71 KB, three CTAs per SM -- 6.87 ms per scene against 6.20 ms: the
+// extra halo rows of the shorter tile cost more than the third CTA's overlap buys.)
 
 #include <cmath>
 
