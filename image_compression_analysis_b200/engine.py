@@ -590,24 +590,34 @@ def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Option
     up = torch.cuda.Stream(dev)
     it = iter(pairs)
 
+    # three device buffer pairs owned by the sweep and reused in turn (pair k lives in slot k % 3): no allocator
+    # in the loop -- a cudaMalloc for a 377 MB cube would synchronise the device in the middle of the pipeline
+    slots = [None, None, None]              # [dr, dt, event "kernels that read this slot are done"]
+    counter = [0]
+
     def start_upload(item):
         ref, tst = item
         name = np_dtype or _np_name(ref)
         dtype_code(name)
         hr = ref.view(torch.int16) if ref.dtype == torch.uint16 else ref
         ht = tst.view(torch.int16) if tst.dtype == torch.uint16 else tst
+        k = counter[0] % 3
+        counter[0] += 1
+        slot = slots[k]
+        if slot is None or slot[0].shape != hr.shape or slot[0].dtype != hr.dtype:
+            slot = slots[k] = [torch.empty(hr.shape, dtype=hr.dtype, device=dev),
+                               torch.empty(ht.shape, dtype=ht.dtype, device=dev), None]
+            up.wait_stream(comp)            # fresh memory may have had users on the compute stream
         with torch.cuda.stream(up):
-            dr = torch.empty(hr.shape, dtype=hr.dtype, device=dev)
-            dt = torch.empty(ht.shape, dtype=ht.dtype, device=dev)
-            dr.copy_(hr, non_blocking=True)
-            dt.copy_(ht, non_blocking=True)
+            if slot[2] is not None:
+                up.wait_event(slot[2])      # the pair that lived here three uploads ago has been evaluated
+            slot[0].copy_(hr, non_blocking=True)
+            slot[1].copy_(ht, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up)
-        dr.record_stream(comp)          # allocated on the upload stream, consumed on the compute stream
-        dt.record_stream(comp)
         shape = tuple(hr.shape)
         B, H, W = (shape[0], shape[1], shape[2]) if layout == "bsq" else (shape[2], shape[0], shape[1])
-        return DevicePair(dr, dt, name, layout, B, H, W), ev
+        return DevicePair(slot[0], slot[1], name, layout, B, H, W), ev, slot
 
     def finish_one(entry):
         P, host, ev = entry
@@ -624,13 +634,15 @@ def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Option
     except StopIteration:
         return
     while nxt is not None:
-        pair, ev = nxt
+        pair, ev, dslot = nxt
         try:
             nxt = start_upload(next(it))            # the next pair's copies queue up behind this pair's
         except StopIteration:
             nxt = None
         comp.wait_event(ev)
         P = evaluate(pair, want)
+        dslot[2] = torch.cuda.Event()
+        dslot[2].record(comp)                       # the slot may be overwritten once these kernels are done
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             P.allreduce_(group)
         host = ring[slot % len(ring)]
