@@ -362,7 +362,6 @@ def main():
     # ---- end-to-end arm: pinned host cubes -> public API -> metrics dict -------------------------
     e2e = None
     if not args.no_e2e:
-        import image_compression_analysis_b200 as dm
         host = []
         for i in range(2):
             r = torch.empty((ROWS, WIDTH, BANDS), dtype=torch.int16).pin_memory()

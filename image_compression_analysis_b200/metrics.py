@@ -25,8 +25,7 @@ import numpy as np
 import torch
 
 from . import finish
-from .engine import DevicePair, Partials, Want, dtype_code, evaluate, require_cuda, to_device
-from .raster_io import explicit_mask, open_raster
+from .engine import DevicePair, Partials, Want, dtype_code, evaluate, to_device
 
 # ---------------------------------------------------------------------------------------------
 # scalar metrics (run_codec.py:55-80)
@@ -198,7 +197,6 @@ def compute_sam_sid_lmse_caseB(ref_path: Path, tst_path: Path, valid: Optional[n
 def sobel_mag(img: np.ndarray) -> np.ndarray:
     """3x3 Sobel gradient magnitude of one (H,W) band as float64 (run_codec.py:123-137), on the GPU.
     Integer samples of up to 16 bits (what the path sees); other sample types are an error, not a CPU detour."""
-    import ctypes as C
     from ._lib import check, lib
     from .engine import _ptr, _stream_ptr
     img = np.asarray(img)

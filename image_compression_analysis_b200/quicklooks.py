@@ -15,14 +15,14 @@ from __future__ import annotations
 
 import argparse
 from pathlib import Path
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 
 from . import finish
 from ._lib import DM_VALID_QUICKLOOK
 from .engine import DevicePair, Want, evaluate, to_device
-from .raster_io import explicit_mask, open_raster, uint8_dtype
+from .raster_io import open_raster, uint8_dtype
 
 RGB_ORDER = [3, 2, 1]  # 1-based band indices, as in the reference
 
