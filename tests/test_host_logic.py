@@ -229,3 +229,21 @@ def test_header_is_plain_c():
                 ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_small_host_helpers():
+    """Best-effort NUMA binding never raises; stretch tables cover the whole sample type in bin order."""
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200.engine import bind_host_to_gpu_numa, integral_nodata
+    assert bind_host_to_gpu_numa(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)
+    lut = finish.stretch8_lut(100.0, 200.0, "uint16")
+    assert lut.shape == (65536,) and lut[0] == 0 and lut[100] == 0 and lut[200] == 255 and lut[65535] == 255
+    x = np.arange(65536, dtype=np.int64).astype(np.uint16)
+    want = (np.clip((x.astype(np.float32) - 100.0) / (200.0 - 100.0 + 1e-9), 0, 1) * 255.0).astype(np.uint8)
+    assert np.array_equal(lut, want)
+    li = finish.stretch8_lut(-50.0, 50.0, "int16")          # bin 0 is -32768
+    assert li[0] == 0 and li[32768 - 50] == 0 and li[32768 + 50] >= 254 and li[65535] == 255
+    lb = finish.stretch8_lut(0.0, 255.0, "uint8")
+    assert lb.shape == (65536,) and lb[255] >= 254 and not lb[256:].any()
+    assert integral_nodata(-32768.0, "int16") == -32768 and integral_nodata(float("nan"), "int16") is None
+    assert integral_nodata(70000, "uint16") is None and integral_nodata(1.5, "uint16") is None
