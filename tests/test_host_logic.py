@@ -247,3 +247,17 @@ def test_small_host_helpers():
     assert lb.shape == (65536,) and lb[255] >= 254 and not lb[256:].any()
     assert integral_nodata(-32768.0, "int16") == -32768 and integral_nodata(float("nan"), "int16") is None
     assert integral_nodata(70000, "uint16") is None and integral_nodata(1.5, "uint16") is None
+
+
+def test_c_consumer_links_and_runs(built_lib, tmp_path):
+    """examples/c_abi_example.c: a plain C program compiles against include/dm_b200.h, links libdm_b200.so and
+    runs -- without a GPU it must report the library's error text and exit 0 (no CPU path, no crash)."""
+    exe = tmp_path / "dm_example"
+    pkg = ROOT / "image_compression_analysis_b200"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}",
+                        str(ROOT / "examples" / "c_abi_example.c"), f"-L{pkg}", "-ldm_b200", f"-Wl,-rpath,{pkg}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"ABI {built_lib.ABI_VERSION}" in r.stdout
