@@ -15,6 +15,9 @@ import sys
 from pathlib import Path
 
 
+QUICKLOOKS_PLUGIN = Path(__file__).resolve().parent / "plugin" / "quicklooks.py"
+
+
 def bind(run_codec_module) -> None:
     """Rebind the reference module's metric functions to the GPU implementations."""
     import image_compression_analysis_b200 as dm
@@ -39,7 +42,7 @@ def main(argv=None) -> int:
     run_codec = importlib.import_module("run_codec")
     bind(run_codec)
     if "--quicklooks" not in rest:
-        rest = ["--quicklooks", str(Path(__file__).resolve().parent / "quicklooks.py"), *rest]
+        rest = ["--quicklooks", str(QUICKLOOKS_PLUGIN), *rest]
     sys.argv = ["run_codec.py", *rest]
     run_codec.main()
     return 0

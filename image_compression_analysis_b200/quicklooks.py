@@ -288,7 +288,8 @@ def write_error_max8(a_path, b_path, out_path_base, err_max_global=255, err_max_
     return out_g, out_z
 
 
-if __name__ == "__main__":
+def main(argv=None) -> int:
+    """The reference module's command line (quicklooks.py:213-239), used by make_baseline_A.py:189-198."""
     ap = argparse.ArgumentParser(description="RGB quicklook and 8-bit error maps (B200)")
     ap.add_argument("--baseline", required=True, help="Reference multiband image")
     ap.add_argument("--out", help="Output 8-bit RGB from baseline (optional)")
@@ -298,7 +299,7 @@ if __name__ == "__main__":
     ap.add_argument("--err-max-zoom", type=int, default=None)
     ap.add_argument("--rgb-order", nargs=3, type=int, default=RGB_ORDER)
     ap.add_argument("--rgb-pct", nargs=2, type=float, default=(2, 98))
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     p = Path(args.baseline)
     if args.out:
         prm = stretch_params_from_baseline(p, rgb_order=args.rgb_order, pct=tuple(args.rgb_pct))
@@ -307,3 +308,8 @@ if __name__ == "__main__":
         base = Path(args.err_out_base) if args.err_out_base else Path(args.baseline).with_suffix("")
         write_error_max8(a_path=args.baseline, b_path=args.error_against, out_path_base=base.as_posix(),
                          err_max_global=args.err_max_global, err_max_zoom=args.err_max_zoom)
+    return 0
+
+
+if __name__ == "__main__":          # python -m image_compression_analysis_b200.quicklooks ...
+    raise SystemExit(main())
