@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -59,6 +59,7 @@ SYMBOLS = {
     "dm_device_sm_count": (C.c_int, []),
     "dm_launch_count": (C.c_int64, []),
     "dm_launch_chaining": (None, [C.c_int32]),
+    "dm_fused_bip_variant": (C.c_int, [C.c_int32]),
     "dm_validity": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P]),
     "dm_fused_stats": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
     "dm_workspace_bytes": (C.c_int64, []),
@@ -69,9 +70,9 @@ SYMBOLS = {
     "dm_fused_bsq": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "dm_sobel_mag": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "dm_sobel_nblocks": (C.c_int, []),
-    "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "dm_ssim_nblocks": (C.c_int, []),
-    "dm_ssim_gauss": (C.c_int, [C.POINTER(DmPair), C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    "dm_ssim_gauss": (C.c_int, [C.POINTER(DmPair), C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "dm_combine_partials": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_bip_to_bsq": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),
     "dm_band_hist": (C.c_int, [C.POINTER(DmCube), C.POINTER(C.c_int32), C.c_int32, _P, C.c_int32, _P, _P]),

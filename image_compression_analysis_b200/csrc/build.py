@@ -22,6 +22,8 @@ LIB = PKG / "libdm_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", str(ROOT / "include"), "-I", str(HERE)]
+if os.environ.get("DM_DEBUG_HOOKS"):      # experiment build for tools/probe_fused.py (build with --force, and again without)
+    FLAGS.append("-DDM_DEBUG_HOOKS")
 
 
 def _stale(target: Path, deps) -> bool:

@@ -15,6 +15,7 @@ int cuda_fail(cudaError_t e, const char* what);     // DM_ECUDA with the CUDA er
 int sm_count();                                     // SMs of the current device (cached), <0 on error
 void count_launch();                                // one more kernel launched (dm_launch_count)
 bool launch_chaining();                             // dm_launch_chaining() state of this thread
+int fused_bip_variant();                            // dm_fused_bip_variant() state of this thread
 
 #define DM_CUDA(expr)                                              \
   do {                                                             \
@@ -35,9 +36,13 @@ static inline int elem_bytes(int dtype) { return dtype == DM_U8 ? 1 : 2; }
 // partials and the arrival counter of the in-kernel ordered final reduction.  The last block of a
 // launch resets the counter, so consecutive launches on one stream can share a workspace.
 constexpr int kMaxPartialBlocks = 1184;
+constexpr int kMaxCounterBands = 2048;     // per-band arrival counters of the (blocks, bands)-grid stencil kernels
+constexpr int kMaxGroups = 64;             // block groups of the two-level reduction (BIP Sobel kernel)
 struct Workspace {
-  unsigned counter[16];
+  unsigned counter[16];                    // [0] spectral / one-pass kernels, [1] BIP Sobel kernel (final level)
   double part[3 * kMaxPartialBlocks];
+  unsigned band_counter[kMaxCounterBands];
+  unsigned group_counter[kMaxGroups];
 };
 
 // launchers implemented in the kernel translation units
@@ -62,9 +67,10 @@ int launch_sobel_mag(const void* img, int dtype, int64_t rows, int64_t width, do
 int sobel_nblocks();
 int ssim_nblocks();
 int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0,
-                 int64_t img_rows, double* out, cudaStream_t s);
+                 int64_t img_rows, double* scratch, double* lmse_acc, void* workspace, cudaStream_t s);
 int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t row_end,
-                      int64_t img_row0, int64_t img_rows, double* out, cudaStream_t s);
+                      int64_t img_row0, int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc,
+                      void* workspace, cudaStream_t s);
 int launch_combine_partials(const void* gathered, int world, int64_t records, int64_t n_sum, int64_t n_max,
                             int64_t n_f64, void* out, cudaStream_t s);
 int launch_bip_to_bsq(const void* src, void* dst, int elem_bytes, int64_t bands, int64_t rows,
@@ -213,6 +219,54 @@ __device__ __forceinline__ void ordered_block_sum3(double t0, double t1, double 
   if (lane == 0) {
     acc[0] += a0; acc[1] += a1; acc[2] += a2;
     ws->counter[0] = 0;
+  }
+}
+
+// Ordered final reduction for kernels whose grid is (blocks, bands) and whose blocks each hold NV float64
+// partials of ONE band (valid in thread 0).  Block (x, band) stores them at scratch[(band * gridDim.x + x) * NV + v];
+// the block of a band that arrives last adds that band's gridDim.x partials in a fixed order (thread i takes
+// entries i, i + blockDim.x, ...; shuffle tree; warps in order) and ACCUMULATES into acc[v][band].  The result does
+// not depend on which block is last, every band is reduced by a different block (the tail is one short pass over
+// gridDim.x values, not over the whole grid), and no follow-up reduction kernel is needed.  All threads call;
+// `red` is shared scratch of >= NV * 32 doubles.  counter: Workspace::band_counter (zero on entry, reset here).
+template <int NV>
+__device__ __forceinline__ void ordered_band_sum(const double (&t)[NV], double* scratch, unsigned* counter,
+                                                 double* const (&acc)[NV], double* red) {
+  __shared__ unsigned s_last;
+  const int band = blockIdx.y;
+  double* mine = scratch + ((size_t)band * gridDim.x + blockIdx.x) * NV;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) __stcg(mine + v, t[v]);
+    __threadfence();
+    s_last = atomicAdd(&counter[band], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* base = scratch + (size_t)band * gridDim.x * NV;
+  double a[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) a[v] = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) a[v] += __ldcg(base + (size_t)i * NV + v);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    a[v] = warp_sum_f64(a[v]);
+    if (lane == 0) red[v * 32 + warp] = a[v];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double tot = 0.0;
+      for (int w = 0; w < nw; ++w) tot += red[v * 32 + w];
+      acc[v][band] += tot;
+    }
+    counter[band] = 0;
   }
 }
 

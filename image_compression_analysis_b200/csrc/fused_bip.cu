@@ -31,6 +31,16 @@
 #ifndef DM_POLL_NS
 #define DM_POLL_NS 64
 #endif
+// Experiment switches (tools/probe_fused.py: DM_FUSED_DEBUG / DM_POLL_NS / DM_NO_PDL environment variables, A/B
+// branches inside the kernels) exist only in a -DDM_DEBUG_HOOKS build (DM_DEBUG_HOOKS=1 python csrc/build.py).
+// The shipping library reads no environment variable and the branches fold away at compile time.
+#ifdef DM_DEBUG_HOOKS
+#define DM_DBG(g) ((g).debug)
+#define DM_POLL(g) ((g).poll_ns)
+#else
+#define DM_DBG(g) 0
+#define DM_POLL(g) kPollNs
+#endif
 
 namespace dm {
 
@@ -221,7 +231,7 @@ fused_bip_kernel(FusedArgs g) {
       mbar_wait(&empty_bar[s], ph ^ 1u);             // first pass over the ring: passes immediately
       unsigned char* dst = smem + (size_t)s * stage_bytes;
       const int64_t off = t * (int64_t)cube_bytes;
-      if (g.debug == 1) {
+      if (DM_DBG(g) == 1) {
         if (lane == 0) mbar_arrive(&full_bar[s]);
       } else if (t < g.ntiles) {
         if (lane == 0) {
@@ -611,8 +621,8 @@ fused_ct_kernel(FusedArgs g) {
   // lives in stage it % kStages (full tiles only; the launcher hands a partial tile to the generic kernel)
   const int my_tiles = (int64_t)blockIdx.x < g.ntiles ? (int)((g.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
   // no per-pixel output requested (stats only): the pixel warps just hand their stages back
-  const int dbg = g.debug | ((ERR || g.want_sam) ? 0 : 4);
-  const uint32_t poll_ns = g.poll_ns;
+  const int dbg = DM_DBG(g) | ((ERR || g.want_sam) ? 0 : 4);
+  const uint32_t poll_ns = DM_POLL(g);
   const uint32_t ring = smem_u32(smem);
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
 
@@ -987,7 +997,7 @@ validity_ct_kernel(ValArgs g) {
   }
   __syncthreads();
   const int my_tiles = (int64_t)blockIdx.x < g.ntiles ? (int)((g.ntiles - 1 - blockIdx.x) / gridDim.x) + 1 : 0;
-  const uint32_t poll_ns = g.poll_ns;
+  const uint32_t poll_ns = DM_POLL(g);
   const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
   const uint32_t tx_bytes = (g.ref_has ? G::CUBE : 0) + (g.tst_has ? G::CUBE : 0);
 
@@ -1125,7 +1135,11 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
   if (grid > g.ntiles) grid = g.ntiles;
   // programmatic dependent launch only while the caller has switched launch chaining on (dm_launch_chaining):
   // a chained launch reads its inputs before the preceding kernel's writes are guaranteed to be flushed
+#ifdef DM_DEBUG_HOOKS
   static const bool pdl_allowed = []() { const char* e = getenv("DM_NO_PDL"); return !(e && atoi(e)); }();
+#else
+  constexpr bool pdl_allowed = true;
+#endif
   const bool pdl = pdl_allowed && launch_chaining();
 #define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
   do {                                                                                                \
@@ -1178,10 +1192,14 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   g.lut_g = lut_g; g.cap_g = cap_g; g.err8_g = err8_g; g.hist8_g = err8_g ? hist8_g : nullptr;
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
   g.want_sam = want_sam; g.spec_acc = want_sam ? spectral_acc : nullptr; g.ws = workspace;
+  g.debug = 0; g.poll_ns = kPollNs;
+#ifdef DM_DEBUG_HOOKS
   { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
   { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
+#endif
   if (g.npix <= 0) return DM_OK;
-  const bool force_generic = (g.debug & 8) != 0;
+  const int variant = fused_bip_variant();             // dm_fused_bip_variant(): 0 auto | 12 | 23 | 1 = run-time-geometry kernel
+  const bool force_generic = variant == 1 || (g.debug & 8) != 0;
   // (the specialised kernel bulk-copies the tile's 64 mask bytes: the plane must be 16-byte aligned)
   if (B == 180 && g.npix >= kTilePixels && !force_generic && !(reinterpret_cast<uintptr_t>(plane) & 15)) {
     // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
@@ -1190,8 +1208,9 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
     // Two builds of the kernel: 12 band warps (ldmatrix.x4, 96 registers) or 23 (ldmatrix.x2, 64 registers).
     // Measured in a sweep (bench.py): plain stats + SAM 135.5 us with 23 band warps against 137.2 us; with
     // error planes or a validity plane the 12-warp build wins (163 / 176 us against 165 / 190 us).
-    // DM_FUSED_DEBUG bit 16 flips the choice (A/B runs, and the tests cover both builds).
-    const bool narrow = (!plane && !errmax_out && !err8_g && !err8_z) != ((g.debug & 16) != 0);
+    // dm_fused_bip_variant(12 | 23) pins the choice (A/B runs, and the tests cover both builds).
+    bool narrow = (!plane && !errmax_out && !err8_g && !err8_z) != ((g.debug & 16) != 0);
+    if (variant == 12) narrow = false; else if (variant == 23) narrow = true;
     int rc = narrow ? run_ct<180, 2>(g, p.dtype, s) : run_ct<180, 4>(g, p.dtype, s);
     if (rc != DM_OK || done == g.npix) return rc;
     g.ref = static_cast<const char*>(g.ref) + done * B * 2;
@@ -1219,7 +1238,10 @@ int64_t launch_validity_ct(const dm_pair_t& p, const uint8_t* valid_in, uint8_t*
   g.ref = p.ref; g.tst = p.tst; g.valid_in = valid_in; g.plane = plane_out; g.counts = counts;
   g.ntiles = npix / kTilePixels;
   g.ref_has = p.ref_has_nodata; g.ref_nd = p.ref_nodata; g.tst_has = p.tst_has_nodata; g.tst_nd = p.tst_nodata;
+  g.poll_ns = kPollNs;
+#ifdef DM_DEBUG_HOOKS
   { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
+#endif
   const int sms = sm_count();
   if (sms < 0) { *status = DM_ECUDA; return 0; }
   int64_t grid = sms;

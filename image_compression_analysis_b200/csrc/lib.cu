@@ -15,6 +15,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local bool g_chaining = false;
 bool launch_chaining() { return g_chaining; }
 void set_launch_chaining(bool on) { g_chaining = on; }
+static thread_local int g_bip_variant = 0;
+int fused_bip_variant() { return g_bip_variant; }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -53,6 +55,11 @@ extern "C" {
 
 int dm_abi_version(void) { return DM_ABI_VERSION; }
 void dm_launch_chaining(int32_t on) { dm::set_launch_chaining(on != 0); }
+int dm_fused_bip_variant(int32_t v) {
+  if (v != 0 && v != 1 && v != 12 && v != 23) return fail(DM_EARG, "dm_fused_bip_variant: 0 (auto), 1 (run-time geometry), 12 or 23 band warps");
+  dm::g_bip_variant = v;
+  return DM_OK;
+}
 const char* dm_last_error(void) { return g_err; }
 int dm_device_sm_count(void) { return sm_count(); }
 int64_t dm_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
@@ -105,18 +112,20 @@ int dm_sobel_mag(const void* img, int32_t dtype, int64_t rows, int64_t width, do
 int dm_sobel_nblocks(void) { return sobel_nblocks(); }
 
 int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,
-                  int64_t img_rows, double* out, void* stream) {
+                  int64_t img_rows, double* scratch, double* lmse_acc, void* workspace, void* stream) {
   if (!p) return fail(DM_EARG, "dm_sobel_lmse: null pair");
-  return launch_sobel(*p, row_begin, row_end, img_row0, img_rows, out, static_cast<cudaStream_t>(stream));
+  return launch_sobel(*p, row_begin, row_end, img_row0, img_rows, scratch, lmse_acc, workspace,
+                      static_cast<cudaStream_t>(stream));
 }
 
 int dm_ssim_nblocks(void) { return ssim_nblocks(); }
 
 int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
-                  int64_t img_row0, int64_t img_rows, double* out, void* stream) {
+                  int64_t img_row0, int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc,
+                  void* workspace, void* stream) {
   if (!p) return fail(DM_EARG, "dm_ssim_gauss: null pair");
-  return launch_ssim_gauss(*p, data_range, row_begin, row_end, img_row0, img_rows, out,
-                           static_cast<cudaStream_t>(stream));
+  return launch_ssim_gauss(*p, data_range, row_begin, row_end, img_row0, img_rows, scratch, sum_acc, cnt_acc,
+                           workspace, static_cast<cudaStream_t>(stream));
 }
 
 int dm_combine_partials(const void* gathered, int32_t world, int64_t records, int64_t n_sum, int64_t n_max, int64_t n_f64,

@@ -4,7 +4,8 @@
 // (/root/reference/tools/run_codec.py:123-137, 341-346).  gx, gy are exact integers
 // (|g| <= 4*65535), gx^2+gy^2 < 2^38 is exact in float64 and the square root is faithfully rounded
 // (sobel_mag2), so every per-pixel term equals the reference's to the last bit or two; the order of the
-// final float64 sum differs (block-ordered partials, reduced on the host).
+// final float64 sum differs (block-ordered partials, added in a fixed order by the blocks that finish last and
+// accumulated into the caller's per-band sums: no follow-up reduction kernel).
 //
 // BSQ: shared-memory tiled, a block stages a (32+2) x (32+2) tile of both cubes once and every sample is
 // read from HBM ~1.13 times.  BIP (16-bit samples, even band count): no transposition -- a thread owns one
@@ -18,7 +19,10 @@ namespace dm {
 
 namespace {
 
-constexpr int kSobBlocks = 296;   // partial slots per band (fixed: layout must not depend on the device)
+constexpr int kSobBlocks = 296;   // blocks per band (fixed: the summation order must not depend on the device)
+constexpr int kSobGroup = 8;      // BIP kernel: blocks per group of the two-level final sum
+constexpr int kSobGroups = (kSobBlocks + kSobGroup - 1) / kSobGroup;
+static_assert(kSobGroups <= kMaxGroups, "Workspace::group_counter too small");
 constexpr int TW = 32, TH = 32;
 
 // |grad| = sqrt(gx^2 + gy^2) for integer gradients (|g| <= 4*65535).  The sum of squares is an exact
@@ -47,10 +51,11 @@ __device__ __forceinline__ double sobel_mag2(int gx, int gy) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t band_stride, int64_t width,
-                  int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows, double* out) {
+                  int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows, double* scratch,
+                  double* lmse_acc, void* workspace) {
   __shared__ int sa[TH + 2][TW + 2 + 1];
   __shared__ int sr[TH + 2][TW + 2 + 1];
-  __shared__ double red[8];
+  __shared__ double red[32];
   const int band = blockIdx.y;
   const T* A = ref + (int64_t)band * band_stride;
   const T* R = tst + (int64_t)band * band_stride;
@@ -104,11 +109,13 @@ sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   acc = warp_sum_f64(acc);
   if (tx == 0) red[ty] = acc;
   __syncthreads();
+  double t[1] = {0.0};
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    out[(int64_t)band * kSobBlocks + blockIdx.x] = t;
+    for (int w = 0; w < 8; ++w) t[0] += red[w];
   }
+  __syncthreads();
+  double* const accs[1] = {lmse_acc};
+  ordered_band_sum<1>(t, scratch, static_cast<Workspace*>(workspace)->band_counter, accs, red);
 }
 
 
@@ -133,8 +140,10 @@ struct ColTerms {                     // separable Sobel terms of one image colu
 template <int DT>
 __global__ void __launch_bounds__(kBipThreads, 2)
 sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restrict__ tst, int wp, int wpad, int64_t width,
-                      int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows, double* out) {
+                      int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows, double* scratch,
+                      double* lmse_acc, void* workspace) {
   __shared__ double red[kBipThreads][2];
+  __shared__ unsigned s_flag;
   const int groups = kBipThreads / wpad;
   const int grp = threadIdx.x / wpad, w = threadIdx.x - grp * wpad;
   const bool active = grp < groups && w < wp;
@@ -203,12 +212,54 @@ sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restri
   }
   red[threadIdx.x][0] = acc0; red[threadIdx.x][1] = acc1;
   __syncthreads();
+  // Two-level ordered final sum.  Every block holds a partial for EVERY band, so a single "last block" would have
+  // to add gridDim.x x bands values by itself; instead the block that finishes last in each group of kSobGroup
+  // blocks adds the group's partials (level 1, in block order) and the group that finishes last adds the group
+  // sums (level 2, in group order) into the caller's per-band accumulators.  Thread w owns bands 2w, 2w+1.
+  Workspace* ws = static_cast<Workspace*>(workspace);
+  const int nb = 2 * wp, grp_id = blockIdx.x / kSobGroup;
+  const int ngroups = (gridDim.x + kSobGroup - 1) / kSobGroup;
+  const int gsize = min(kSobGroup, (int)gridDim.x - grp_id * kSobGroup);
+  double* l1 = scratch;                                    // [gridDim.x][bands]
+  double* l2 = scratch + (size_t)gridDim.x * nb;           // [ngroups][bands]
   if (threadIdx.x < wp) {
     double t0 = 0.0, t1 = 0.0;
     for (int gi = 0; gi < groups; ++gi) { t0 += red[gi * wpad + threadIdx.x][0]; t1 += red[gi * wpad + threadIdx.x][1]; }
-    out[(int64_t)(2 * threadIdx.x) * kSobBlocks + blockIdx.x] = t0;
-    out[(int64_t)(2 * threadIdx.x + 1) * kSobBlocks + blockIdx.x] = t1;
+    __stcg(reinterpret_cast<double2*>(l1 + (size_t)blockIdx.x * nb) + threadIdx.x, make_double2(t0, t1));
+    __threadfence();
   }
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = atomicAdd(&ws->group_counter[grp_id], 1u) == (unsigned)gsize - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  if (threadIdx.x < wp) {
+    double u0 = 0.0, u1 = 0.0;
+    for (int k = 0; k < gsize; ++k) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(l1 + (size_t)(grp_id * kSobGroup + k) * nb) + threadIdx.x);
+      u0 += v.x; u1 += v.y;
+    }
+    __stcg(reinterpret_cast<double2*>(l2 + (size_t)grp_id * nb) + threadIdx.x, make_double2(u0, u1));
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ws->group_counter[grp_id] = 0;
+    s_flag = atomicAdd(&ws->counter[1], 1u) == (unsigned)ngroups - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  if (threadIdx.x < wp) {
+    double u0 = 0.0, u1 = 0.0;
+    for (int k = 0; k < ngroups; ++k) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(l2 + (size_t)k * nb) + threadIdx.x);
+      u0 += v.x; u1 += v.y;
+    }
+    lmse_acc[2 * threadIdx.x] += u0;
+    lmse_acc[2 * threadIdx.x + 1] += u1;
+  }
+  if (threadIdx.x == 0) ws->counter[1] = 0;
 }
 
 // ---- magnitude map (the reference's sobel_mag as a function of its own, run_codec.py:123-137) -----------
@@ -255,17 +306,18 @@ int launch_sobel_mag(const void* img, int dtype, int64_t rows, int64_t width, do
   return DM_OK;
 }
 
-int sobel_nblocks() { return kSobBlocks; }
+int sobel_nblocks() { return kSobBlocks + kSobGroups; }   // scratch slots per band: block partials + group sums
 
 int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t img_row0, int64_t img_rows,
-                 double* out, cudaStream_t s) {
-  if (!p.ref || !p.tst || !out) return fail(DM_EARG, "dm_sobel_lmse: null pointer");
+                 double* scratch, double* lmse_acc, void* workspace, cudaStream_t s) {
+  if (!p.ref || !p.tst || !scratch || !lmse_acc || !workspace) return fail(DM_EARG, "dm_sobel_lmse: null pointer");
+  if ((reinterpret_cast<uintptr_t>(scratch) & 15) != 0) return fail(DM_EARG, "dm_sobel_lmse: scratch must be 16-byte aligned");
   if (p.layout != DM_BSQ && p.layout != DM_BIP) return fail(DM_EARG, "dm_sobel_lmse: bad layout");
   if (p.layout == DM_BIP && (p.dtype == DM_U8 || p.bands % 2 != 0 || p.bands > 2 * kBipThreads ||
                              (reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) % 4 != 0))
     return fail(DM_EUNSUPPORTED, "dm_sobel_lmse: BIP needs 16-bit samples, an even band count and 4-byte aligned cubes "
                                  "(otherwise transpose with dm_bip_to_bsq)");
-  if (p.bands <= 0 || p.bands > 65535 || p.width <= 0) return fail(DM_EARG, "dm_sobel_lmse: bad geometry");
+  if (p.bands <= 0 || p.bands > kMaxCounterBands || p.width <= 0) return fail(DM_EARG, "dm_sobel_lmse: bad geometry (1..2048 bands)");
   if (row_begin < 0 || row_end > p.rows || row_begin > row_end || img_row0 < 0 || img_row0 + p.rows > img_rows)
     return fail(DM_EARG, "dm_sobel_lmse: bad row range");
   // halo rows must be present unless the strip touches the image border
@@ -275,17 +327,18 @@ int launch_sobel(const dm_pair_t& p, int64_t row_begin, int64_t row_end, int64_t
     const int wp = (int)(p.bands / 2), wpad = (wp + 31) / 32 * 32;
     if (p.dtype == DM_I16)
       sobel_lmse_bip_kernel<DM_I16><<<kSobBlocks, kBipThreads, 0, s>>>(static_cast<const uint32_t*>(p.ref), static_cast<const uint32_t*>(p.tst),
-                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, out);
+                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, scratch, lmse_acc, workspace);
     else
       sobel_lmse_bip_kernel<DM_U16><<<kSobBlocks, kBipThreads, 0, s>>>(static_cast<const uint32_t*>(p.ref), static_cast<const uint32_t*>(p.tst),
-                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, out);
+                                                                      wp, wpad, p.width, row_begin, row_end, img_row0, img_rows, scratch, lmse_acc, workspace);
     DM_LAUNCH_CHECK("sobel_lmse_bip");
     return DM_OK;
   }
   const dim3 grid(kSobBlocks, (unsigned)p.bands);
 #define DM_SOBEL(T)                                                                                          \
   sobel_lmse_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(p.ref), static_cast<const T*>(p.tst),      \
-                                            p.band_stride, p.width, row_begin, row_end, img_row0, img_rows, out)
+                                            p.band_stride, p.width, row_begin, row_end, img_row0, img_rows, scratch, \
+                                            lmse_acc, workspace)
   switch (p.dtype) {
     case DM_U8: DM_SOBEL(uint8_t); break;
     case DM_U16: DM_SOBEL(uint16_t); break;

@@ -45,12 +45,13 @@ struct Taps { double w[2 * RAD + 1]; };
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t band_stride, int64_t width,
-                  int64_t r_lo, int64_t r_hi, int64_t buf_rows, Taps taps, double c1, double c2, double* out) {
+                  int64_t r_lo, int64_t r_hi, int64_t buf_rows, Taps taps, double c1, double c2, double* scratch,
+                  double* sum_acc, double* cnt_acc, void* workspace) {
   extern __shared__ __align__(16) unsigned char ssim_smem[];
   int (*xs)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem);
   int (*ys)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem + IH * (IW + 1) * 4);
   double (*hp)[PH][HP] = reinterpret_cast<double (*)[PH][HP]>(ssim_smem + 2 * IH * (IW + 1) * 4);   // [4][PH][HP]
-  __shared__ double red[2][8];
+  __shared__ double red[2][32];
   const int band = blockIdx.y;
   const T* A = ref + (int64_t)band * band_stride;
   const T* R = tst + (int64_t)band * band_stride;
@@ -165,12 +166,14 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   acc = warp_sum_f64(acc); cnt = warp_sum_f64(cnt);
   if (tx == 0) { red[0][ty] = acc; red[1][ty] = cnt; }
   __syncthreads();
+  double t[2] = {0.0, 0.0};
   if (threadIdx.x == 0) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int w = 0; w < 8; ++w) { t0 += red[0][w]; t1 += red[1][w]; }
-    out[((int64_t)band * kSsimBlocks + blockIdx.x) * 2 + 0] = t0;
-    out[((int64_t)band * kSsimBlocks + blockIdx.x) * 2 + 1] = t1;
+    for (int w = 0; w < 8; ++w) { t[0] += red[0][w]; t[1] += red[1][w]; }
   }
+  __syncthreads();
+  // the band's last block adds the band's block partials in a fixed order and accumulates {sum of S, count}
+  double* const accs[2] = {sum_acc, cnt_acc};
+  ordered_band_sum<2>(t, scratch, static_cast<Workspace*>(workspace)->band_counter, accs, &red[0][0]);
 }
 
 #undef DM_TAP
@@ -180,10 +183,11 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
 int ssim_nblocks() { return kSsimBlocks; }
 
 int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t row_end, int64_t img_row0,
-                      int64_t img_rows, double* out, cudaStream_t s) {
-  if (!p.ref || !p.tst || !out) return fail(DM_EARG, "dm_ssim_gauss: null pointer");
+                      int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc, void* workspace,
+                      cudaStream_t s) {
+  if (!p.ref || !p.tst || !scratch || !sum_acc || !cnt_acc || !workspace) return fail(DM_EARG, "dm_ssim_gauss: null pointer");
   if (p.layout != DM_BSQ) return fail(DM_EUNSUPPORTED, "dm_ssim_gauss: BSQ only (transpose with dm_bip_to_bsq)");
-  if (p.bands <= 0 || p.bands > 65535 || p.width <= 0) return fail(DM_EARG, "dm_ssim_gauss: bad geometry");
+  if (p.bands <= 0 || p.bands > kMaxCounterBands || p.width <= 0) return fail(DM_EARG, "dm_ssim_gauss: bad geometry (1..2048 bands)");
   if (row_begin < 0 || row_end > p.rows || row_begin > row_end || img_row0 < 0 || img_row0 + p.rows > img_rows)
     return fail(DM_EARG, "dm_ssim_gauss: bad row range");
   // counted buffer rows: inside [row_begin,row_end) and inside the 5-px crop of the image
@@ -202,7 +206,8 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
   do {                                                                                                       \
     DM_CUDA(cudaFuncSetAttribute(ssim_gauss_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSsimSmem)); \
     ssim_gauss_kernel<T><<<grid, 256, kSsimSmem, s>>>(static_cast<const T*>(p.ref), static_cast<const T*>(p.tst), \
-                                                      p.band_stride, p.width, r_lo, r_hi, p.rows, taps, c1, c2, out); \
+                                                      p.band_stride, p.width, r_lo, r_hi, p.rows, taps, c1, c2, scratch, \
+                                                      sum_acc, cnt_acc, workspace);                           \
   } while (0)
   switch (p.dtype) {
     case DM_U8: DM_SSIM(uint8_t); break;

@@ -433,6 +433,20 @@ def workspace(device) -> torch.Tensor:
     return w
 
 
+_SCRATCH: Dict[Tuple[int, int, str], torch.Tensor] = {}
+
+
+def _scratch(device, what: str, n_f64: int) -> torch.Tensor:
+    """Per-(device, stream) float64 scratch of the stencil kernels' block partials (contents irrelevant between
+    launches; launches on one stream are ordered): allocated once, grown on demand -- no allocation in a sweep."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream().cuda_stream, what)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < n_f64:
+        t = _SCRATCH[key] = torch.empty(max(n_f64, 1), dtype=torch.float64, device=device)
+    return t
+
+
 def needs_plane(pair: DevicePair, valid) -> bool:
     return valid is not None or pair.ref_nodata is not None or pair.tst_nodata is not None
 
@@ -546,32 +560,29 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
                             1 if want.sam else 0, 1 if want.sid else 0, _ptr(P.spec), _ptr(ws), st))
     if want.lmse or want.ssim_gauss:
         r0, r1 = rows if rows is not None else (0, pair.rows)
+        ws = ws if ws is not None else workspace(dev)
         bsq = None
         if want.lmse:
-            nb = L.dm_sobel_nblocks()
-            buf = torch.empty(pair.bands * nb, dtype=torch.float64, device=dev)
-            # BIP cubes of 16-bit samples go straight in (a thread owns two bands of the spectrum); the rest
-            # of the layouts are transposed first
-            rc = L.dm_sobel_lmse(C.byref(cp), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st) \
+            # the kernels add their block partials in a fixed order themselves (the blocks that finish last) and
+            # accumulate into P.lmse: no reduction kernels behind them.  BIP cubes of 16-bit samples go straight in
+            # (a thread owns two bands of the spectrum); the rest of the layouts are transposed first
+            buf = _scratch(dev, "sobel", pair.bands * L.dm_sobel_nblocks())
+            rc = L.dm_sobel_lmse(C.byref(cp), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), _ptr(P.lmse), _ptr(ws), st) \
                 if pair.layout == "bip" else _lib.DM_EUNSUPPORTED
             if rc == _lib.DM_EUNSUPPORTED:
                 bsq = pair.as_bsq()
                 cb = bsq.c_pair()
-                rc = L.dm_sobel_lmse(C.byref(cb), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st)
+                rc = L.dm_sobel_lmse(C.byref(cb), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), _ptr(P.lmse), _ptr(ws), st)
             check(rc)
-            P.lmse.add_(buf.view(pair.bands, nb).sum(dim=1))
         if want.ssim_gauss and bsq is None:
             bsq = pair.as_bsq()
             cb = bsq.c_pair()
         if want.ssim_gauss:
             if data_range is None:
                 raise ValueError("ssim_gauss needs data_range (the peak L of the SSIM constants)")
-            nb = L.dm_ssim_nblocks()
-            buf = torch.empty(pair.bands * nb * 2, dtype=torch.float64, device=dev)
-            check(L.dm_ssim_gauss(C.byref(cb), float(data_range), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf), st))
-            v = buf.view(pair.bands, nb, 2).sum(dim=1)
-            P.ssimw_sum.add_(v[:, 0])
-            P.ssimw_cnt.add_(v[:, 1])
+            buf = _scratch(dev, "ssim", pair.bands * L.dm_ssim_nblocks() * 2)
+            check(L.dm_ssim_gauss(C.byref(cb), float(data_range), r0, r1, pair.img_row0, pair.img_rows, _ptr(buf),
+                                  _ptr(P.ssimw_sum), _ptr(P.ssimw_cnt), _ptr(ws), st))
     return P
 
 

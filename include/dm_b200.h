@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 7
+#define DM_ABI_VERSION 8
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -156,6 +156,11 @@ int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
  * when the inputs of a launch are not produced by the kernel issued immediately before it on the same stream
  * (a sweep over cubes that are already resident: engine.PreparedFused). */
 void dm_launch_chaining(int32_t on);
+/* Which build of the one-pass BIP kernel dm_fused_bip launches for 180-band cubes (thread-local, default 0):
+ * 0 = the measured choice (23 band warps for plain statistics + SAM, 12 with planes or a validity plane),
+ * 12 / 23 = pin that build, 1 = the run-time-geometry kernel that serves every other band count.  For A/B
+ * measurements and for the parity tests, which cover every build. */
+int dm_fused_bip_variant(int32_t variant);
 int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
                  uint16_t* errmax_out,
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
@@ -177,23 +182,30 @@ int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
  * sum over pixels of (|grad ref| - |grad tst|)^2 with the 3x3 Sobel pair and edge replication.
  * Counts buffer rows [row_begin,row_end); buffer row 0 is image row img_row0 of img_rows, and the
  * buffer must hold one halo row on each side that is not an image border.
- * out: double[bands * dm_sobel_nblocks()] per-(band,block) partials (written, not accumulated). */
+ * lmse_acc: double[bands], ACCUMULATED (caller-zeroed): the per-band sums.  The blocks' float64 partials are
+ * added in a fixed order by the blocks that finish last (inside the kernel), so the result is reproducible
+ * from run to run and no follow-up reduction is needed.
+ * scratch: double[bands * dm_sobel_nblocks()], 16-byte aligned, contents irrelevant; workspace: dm_workspace_bytes()
+ * bytes, zeroed once by the caller (the kernels leave it zeroed), one per stream.  1..2048 bands. */
 /* sobel_mag as a function of its own (run_codec.py:123-137): float64 magnitude map of one (rows, width) plane,
  * 3x3 Sobel pair with edge replication; bit-identical to the reference for 8/16-bit integer samples. */
 int dm_sobel_mag(const void* img, int32_t dtype, int64_t rows, int64_t width, double* out, void* stream);
 int dm_sobel_nblocks(void);
 int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_t img_row0,
-                  int64_t img_rows, double* out, void* stream);
+                  int64_t img_rows, double* scratch, double* lmse_acc, void* workspace, void* stream);
 
 /* Gaussian-window SSIM (addition) --------------------------------------------
  * 11-tap separable Gaussian (sigma 1.5, truncate 3.5), float64, skimage semantics
  * (use_sample_covariance=False), mean over the image cropped by 5 px.  DM_BSQ only.
- * out: double[bands * 2 * dm_ssim_nblocks()] per-(band,block) partials {sum of S, count} over the
- * pixels of buffer rows [row_begin,row_end) that lie inside the crop (written, not accumulated).
- * The buffer must hold 5 halo rows on each side that is not an image border (borders reflect). */
+ * sum_acc / cnt_acc: double[bands] each, ACCUMULATED (caller-zeroed): sum of S and number of pixels over the
+ * pixels of buffer rows [row_begin,row_end) that lie inside the crop; the band's block partials are added in
+ * a fixed order by the band's last block (inside the kernel).
+ * scratch: double[bands * 2 * dm_ssim_nblocks()], contents irrelevant; workspace as for dm_sobel_lmse.
+ * The buffer must hold 5 halo rows on each side that is not an image border.  1..2048 bands. */
 int dm_ssim_nblocks(void);
 int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
-                  int64_t img_row0, int64_t img_rows, double* out, void* stream);
+                  int64_t img_row0, int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc,
+                  void* workspace, void* stream);
 
 /* multi-GPU combine ----------------------------------------------------------------------------
  * After ONE all-gather of every rank's run of `records` flat partial vectors, each

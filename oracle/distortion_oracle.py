@@ -27,6 +27,9 @@ Pinning status
   scikit-image is not installed here; the definition below restates
   skimage.metrics.structural_similarity(gaussian_weights=True, sigma=1.5,
   use_sample_covariance=False) on top of scipy.ndimage.gaussian_filter.
+  ssim_gaussian_band_direct() states the same quantity a second time from the
+  SSIM paper's definition (direct 11 x 11 window sums, no scipy) so that the
+  pin does not rest on one restatement; it is still not skimage itself.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
 arm may import this module.  It is the checker, never the product: the product
@@ -425,6 +428,34 @@ def ssim_gaussian_band(a: np.ndarray, b: np.ndarray, data_range: float) -> float
     s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
     p = SSIMW_RADIUS
     return float(s[p:-p, p:-p].mean(dtype=np.float64))
+
+
+def ssim_gaussian_band_direct(a: np.ndarray, b: np.ndarray, data_range: float) -> float:
+    """SECOND, independent statement of the same definition, straight from the SSIM paper (Wang, Bovik, Sheikh,
+    Simoncelli 2004, eq. 13 with an 11 x 11 circular-symmetric Gaussian window, sigma 1.5, unit sum) with no
+    scipy.ndimage: the 121-term 2-D weighted sums are written out for every window that lies inside the image
+    -- which are exactly the windows skimage keeps after its 5-px crop -- so no boundary rule, no separable
+    filtering and no truncation logic is shared with ssim_gaussian_band().  The two must agree to rounding
+    (tests/test_oracle_golden.py); the CUDA kernel is checked against both.  O(121 N): small images only."""
+    x = a.astype(np.float64)
+    y = b.astype(np.float64)
+    H, W = x.shape
+    r = SSIMW_RADIUS
+    if H <= 2 * r or W <= 2 * r:
+        return float("nan")
+    k = np.arange(-r, r + 1, dtype=np.float64)
+    w2 = np.exp(-(k[:, None] ** 2 + k[None, :] ** 2) / (2.0 * SSIMW_SIGMA ** 2))
+    w2 /= w2.sum()                                  # normalised as a 2-D window
+    oh, ow = H - 2 * r, W - 2 * r
+    ux = np.zeros((oh, ow)); uy = np.zeros((oh, ow)); uxx = np.zeros((oh, ow)); uyy = np.zeros((oh, ow)); uxy = np.zeros((oh, ow))
+    for i in range(2 * r + 1):
+        for j in range(2 * r + 1):
+            xs, ys, w = x[i:i + oh, j:j + ow], y[i:i + oh, j:j + ow], w2[i, j]
+            ux += w * xs; uy += w * ys; uxx += w * (xs * xs); uyy += w * (ys * ys); uxy += w * (xs * ys)
+    c1 = (0.01 * data_range) ** 2
+    c2 = (0.03 * data_range) ** 2
+    s = ((2 * ux * uy + c1) * (2 * (uxy - ux * uy) + c2)) / ((ux * ux + uy * uy + c1) * ((uxx - ux * ux) + (uyy - uy * uy) + c2))
+    return float(s.mean(dtype=np.float64))
 
 
 def ssim_gaussian(ref: np.ndarray, tst: np.ndarray, data_range: Optional[float] = None) -> Dict[str, float]:

@@ -1,0 +1,208 @@
+"""GPU parity at BASELINE sizes the numpy oracle still finishes in seconds.
+
+The goldens are <= 48 x 64 pixels; at that size every grid-stride / software-pipelined loop of the FP64 kernels
+runs at most ONE iteration per block or warp (the Gaussian SSIM kernel has 296 blocks per band, the SID kernel
+strides 9 472 warps, the BIP Sobel kernel marches along x with a one-column prefetch).  The cases here are sized so
+that every block / warp sees several tiles / pixels, and they compare with the oracle, not with another kernel:
+
+  * BASELINE configs[0] and configs[2] at their real size, 1024 x 1024 x 4 (Case A): compute_metrics, the ERR8
+    planes at caps 255 + 32, per-band Gaussian SSIM (608 tiles per band > 296 blocks)
+  * Case B at 256 x 256 x 180, BIP and BSQ, uint16 and int16 + nodata: SAM / SID / LMSE (>= 6 pixels per warp)
+  * the Gaussian SSIM against the SECOND, scipy-free oracle (direct 11 x 11 window sums)
+  * the NVLink peer-memory exchange against NCCL, run -- not skipped -- whenever two GPUs are visible
+
+Bars as everywhere: integers bit-exact, PSNR bit-exact, SSIM / SAM / SID / LMSE / Gaussian SSIM 1e-6 relative."""
+import math
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import goldenio
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _close(g, w, rel=REL):
+    return goldenio.close(g, w, rel=rel)
+
+
+def _check(got, want):
+    for k, w in want.items():
+        if isinstance(w, np.ndarray):
+            assert np.array_equal(got[k], w), k
+            continue
+        g = got[k]
+        if isinstance(w, (int, np.integer)):
+            assert g == int(w), (k, g, w)
+        elif k.startswith("psnr"):
+            assert (math.isnan(g) and math.isnan(w)) or g == w, (k, g, w)
+        else:
+            assert _close(g, w), (k, g, w)
+
+
+def _bip(x):
+    return np.ascontiguousarray(np.moveaxis(x, 0, -1))
+
+
+@pytest.mark.parametrize("mode", ["gauss", "near3", "identical"])
+def test_config1_case_a_tile_full_size_vs_oracle(mode):
+    """configs[0]: Sentinel-2 1024 x 1024 x 4 uint16 12-in-16 tile: every compute_metrics key + MAE + histograms."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import synth
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_a_pair(seed=1, bands=4, height=1024, width=1024, sigma=2.0, mode=mode)
+    want = orc.compute_metrics(ref, dec, hist_bins=256)
+    got = dm.compute_metrics_arrays(ref, dec, hist_bins=256, extras=True)
+    _check(got, want)
+    assert got["lossless"] == (1 if mode == "identical" else 0)
+    # masked (5 % invalid) through the same kernels
+    valid = synth.random_valid_mask(9, 1024, 1024)
+    _check(dm.compute_metrics_arrays(ref, dec, valid), orc.compute_metrics(ref, dec, valid, extras=False))
+
+
+def test_config3_gaussian_ssim_and_err8_full_size_vs_oracle():
+    """configs[2]: per-band Gaussian SSIM of the 1024 x 1024 x 4 tile (19 x 32 = 608 tiles of 54 x 32 per band on
+    296 blocks: every block runs the prefetching tile loop 2-3 times) + the ERR8 quicklooks at caps 255 and 32."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import quicklooks as ql, synth
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_a_pair(seed=3, bands=4, height=1024, width=1024, sigma=2.0)
+    want = orc.ssim_gaussian(ref, dec)               # data range from the cube: 4095 (12-in-16)
+    got = dm.ssim_gaussian_arrays(ref, dec)
+    assert set(got) == set(want)
+    for k in want:
+        assert _close(got[k], want[k]), (k, got[k], want[k])
+    # a heavier distortion (SSIM well below 1) with the full 16-bit constants
+    rng = np.random.default_rng(33)
+    dec2 = np.clip(ref.astype(np.int64) + rng.integers(-3000, 3001, ref.shape), 0, 65535).astype(np.uint16)
+    want = orc.ssim_gaussian(ref, dec2, 65535.0)
+    got = dm.ssim_gaussian_arrays(ref, dec2, 65535.0)
+    for k in want:
+        assert _close(got[k], want[k]), (k, got[k], want[k])
+    assert want["ssimw_band_avg"] < 0.9
+    e = ql.error_max8_arrays(ref, dec, 255, 32)
+    o = orc.error_max8(ref, dec, 255, 32)
+    for k in ("err8_g", "err8_z", "valid"):
+        assert np.array_equal(e[k], o[k]), k
+    assert e["mean_g"] == o["mean_g"] and e["mean_z"] == o["mean_z"]
+    assert _close(e["std_g"], o["std_g"], 1e-12) and _close(e["std_z"], o["std_z"], 1e-12)
+    # all Case-A metrics from one upload (the path bench.py's C3/C4 lines time)
+    allm = dm.all_metrics_arrays(ref, dec, ssim_window=True, hist_bins=256)
+    _check(allm, orc.compute_metrics(ref, dec, hist_bins=256))
+    for k, w in orc.ssim_gaussian(ref, dec).items():
+        assert _close(allm[k], w), (k, allm[k], w)
+
+
+@pytest.mark.parametrize("dtype,L,amp,shape", [("uint16", 4095.0, 48, (2, 64, 96)), ("uint16", 65535.0, 20000, (1, 33, 47)),
+                                               ("int16", 8191.0, 300, (2, 40, 70)), ("uint8", 255.0, 7, (3, 29, 61))])
+def test_gaussian_ssim_vs_second_oracle(dtype, L, amp, shape):
+    """The kernel against the scipy-free statement of the definition (direct 11 x 11 window sums)."""
+    import image_compression_analysis_b200 as dm
+    from oracle import distortion_oracle as orc
+    rng = np.random.default_rng(71)
+    info = np.iinfo(dtype)
+    a = rng.integers(info.min // 2, info.max // 2, size=shape).astype(np.int64)
+    b = np.clip(a + rng.integers(-amp, amp + 1, size=shape), info.min, info.max)
+    a, b = a.astype(dtype), b.astype(dtype)
+    got = dm.ssim_gaussian_arrays(a, b, L)
+    for i in range(shape[0]):
+        w = orc.ssim_gaussian_band_direct(a[i], b[i], L)
+        assert _close(got[f"ssimw_b{i+1}"], w), (i, got[f"ssimw_b{i+1}"], w)
+
+
+_CASEB_CACHE = {}
+
+
+def _caseb_256(dtype):
+    """256 x 256 x 180 EnMAP-like pair + what the oracle says about it (computed once per dtype, ~5 s)."""
+    if dtype in _CASEB_CACHE:
+        return _CASEB_CACHE[dtype]
+    from image_compression_analysis_b200 import synth
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_b_pair(seed=22, bands=180, height=256, width=256, amp=3, dtype=dtype, layout="bsq")
+    kw = {}
+    valid = None
+    if dtype == "int16":
+        nd = -32768
+        rng = np.random.default_rng(23)
+        whole = rng.random((256, 256)) < 0.05
+        ref = synth.plant_nodata(ref, nd, whole, extra_hits=200, seed=1)
+        dec = synth.plant_nodata(dec, nd, whole, extra_hits=200, seed=2)
+        kw = dict(ref_nodata=nd, tst_nodata=nd)
+    # a few pixels with a relative error above the SID kernel's series guard (5 %), zero spectra, and a block of
+    # large errors: the slow branches must be reached from inside the strided loops too
+    rng = np.random.default_rng(24)
+    ys, xs = rng.integers(0, 256, 300), rng.integers(0, 256, 300)
+    lo, hi = (0, 10000) if dtype == "uint16" else (-8000, 8000)
+    dec[:, ys[:150], xs[:150]] = np.clip(dec[:, ys[:150], xs[:150]].astype(np.int64)
+                                         + rng.integers(-900, 901, (180, 150)), lo, hi).astype(dtype)
+    ref[:, ys[150:170], xs[150:170]] = 0
+    dec[:, ys[170:190], xs[170:190]] = 0
+    want = orc.compute_metrics(ref, dec, valid, extras=False, **kw)
+    want.update(orc.compute_sam_sid_lmse_caseB(ref, dec, valid, **kw))
+    err = orc.error_max8(ref, dec, 255, 32, **kw)
+    _CASEB_CACHE.clear()
+    _CASEB_CACHE[dtype] = (ref, dec, kw, want, err)
+    return _CASEB_CACHE[dtype]
+
+
+@pytest.mark.parametrize("layout", ["bip", "bsq"])
+@pytest.mark.parametrize("dtype", ["uint16", "int16"])
+def test_case_b_256x256x180_all_metrics_vs_oracle(dtype, layout):
+    """65 536 pixels x 180 bands: ~7 pixels per warp of the SID kernel, 4 strides of the Sobel blocks, 1 024 tiles
+    of the one-pass kernel on 148 persistent CTAs.  compute_metrics + SAM / SID / LMSE + ERR8 against the oracle,
+    BIP (one-pass kernels) and BSQ (two-pass kernels), uint16 and the real EnMAP int16 + nodata -32768."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import quicklooks as ql
+    ref, dec, kw, want, err = _caseb_256(dtype)
+    r, d = (ref, dec) if layout == "bsq" else (_bip(ref), _bip(dec))
+    got = dm.compute_metrics_arrays(r, d, layout=layout, **kw)
+    got.update(dm.compute_sam_sid_lmse_caseB_arrays(r, d, layout=layout, **kw))
+    _check(got, want)
+    assert want["sid"] > 0 and want["lmse"] > 0 and want["sam_deg"] > 0
+    e = ql.error_max8_arrays(r, d, 255, 32, layout=layout, a_nodata=kw.get("ref_nodata"), b_nodata=kw.get("tst_nodata"))
+    for k in ("err8_g", "err8_z", "valid"):
+        assert np.array_equal(e[k], err[k]), k
+    # everything from one upload
+    allm = dm.all_metrics_arrays(r, d, layout=layout, case_b=True, extras=False, **kw)
+    _check(allm, want)
+
+
+def test_case_b_256_with_caller_mask_vs_oracle():
+    """The caller's `valid` mask (run_codec.py:260-263, :314-319) on the strided kernels: SAM / SID take the mask,
+    LMSE ignores it."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import synth
+    from oracle import distortion_oracle as orc
+    ref, dec, kw, _, _ = _caseb_256("uint16")
+    valid = synth.random_valid_mask(5, 256, 256, 0.3)
+    want = orc.compute_metrics(ref, dec, valid, extras=False)
+    want.update(orc.compute_sam_sid_lmse_caseB(ref, dec, valid))
+    for layout in ("bip", "bsq"):
+        r, d = (ref, dec) if layout == "bsq" else (_bip(ref), _bip(dec))
+        got = dm.compute_metrics_arrays(r, d, valid, layout=layout)
+        got.update(dm.compute_sam_sid_lmse_caseB_arrays(r, d, valid, layout=layout))
+        _check(got, want)
+
+
+def test_p2p_exchange_is_bit_identical_to_nccl_when_two_gpus_are_visible():
+    """tools/check_p2p.py under torchrun: dm_p2p_push / dm_p2p_combine == NCCL all-gather + dm_combine_partials on
+    every rank.  Runs whenever the box shows >= 2 GPUs (the 1-GPU box of the round-end suite cannot)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip(f"{n} GPU visible: the peer-memory exchange needs two (bench.py asserts the same identity "
+                    "on its own records at every N > 1)")
+    world = min(n, 8)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", str(ROOT / "tools" / "check_p2p.py")],
+                       capture_output=True, text=True, timeout=600, env={**os.environ, "MASTER_ADDR": "127.0.0.1"})
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("p2p == nccl: True; same on all ranks: True") == world

@@ -605,21 +605,38 @@ def test_lmse_flat_and_zero_images(layout):
         assert _close(got["sid"], want["sid"]) and _close(got["sam_deg"], want["sam_deg"]), (got, want)
 
 
-@pytest.mark.parametrize("variant", ["16", "0"])
+@pytest.fixture
+def bip_variant():
+    """Pins the build of the one-pass BIP kernel (dm_fused_bip_variant) for one test, restores the default after."""
+    from image_compression_analysis_b200._lib import check, lib
+
+    def pin(v):
+        check(lib().dm_fused_bip_variant(v))
+    yield pin
+    lib().dm_fused_bip_variant(0)
+
+
+@pytest.mark.parametrize("variant", [12, 23, 1])
 @pytest.mark.parametrize("args", [("uint16", 180, 37, 53, 5, False), ("uint16", 180, 64, 64, 65535, True),
                                   ("int16", 180, 40, 41, 30000, True)])
-def test_fused_ct_both_band_warp_layouts(args, variant, monkeypatch):
+def test_fused_ct_both_band_warp_layouts(args, variant, bip_variant):
     """The 180-band kernel exists with 12 band warps (ldmatrix.x4, 96 registers) and with 23 (ldmatrix.x2, 64
-    registers); DM_FUSED_DEBUG bit 16 flips the default.  Both must match the oracle."""
-    monkeypatch.setenv("DM_FUSED_DEBUG", variant)
+    registers), next to the run-time-geometry kernel (1); dm_fused_bip_variant pins one.  All must match the oracle."""
+    bip_variant(variant)
     test_fused_bip_vs_oracle(*args)
 
 
-@pytest.mark.parametrize("variant", ["16", "0"])
-def test_nodata_180_bands_both_band_warp_layouts(variant, monkeypatch):
-    monkeypatch.setenv("DM_FUSED_DEBUG", variant)
+@pytest.mark.parametrize("variant", [12, 23, 1])
+def test_nodata_180_bands_both_band_warp_layouts(variant, bip_variant):
+    bip_variant(variant)
     test_nodata_180_bands_vs_oracle("int16", -32768, True, False)
     test_nodata_180_bands_vs_oracle("uint16", 65535, True, False)
+
+
+def test_fused_bip_variant_rejects_unknown_values():
+    from image_compression_analysis_b200 import _lib
+    assert _lib.lib().dm_fused_bip_variant(7) == _lib.DM_EARG
+    assert _lib.lib().dm_fused_bip_variant(0) == _lib.DM_OK
 
 
 @pytest.mark.parametrize("layout", ["bsq", "bip"])

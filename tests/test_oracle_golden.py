@@ -74,3 +74,17 @@ def test_gaussian_taps_are_scipy_taps():
     assert taps.size == 11
     assert np.allclose(resp[15:26], taps, rtol=0, atol=1e-17)
     assert abs(taps[5] - 0.266011724862) < 1e-11 and abs(taps[0] - 0.001028380084) < 1e-11
+
+
+@pytest.mark.parametrize("dtype,L,amp", [("uint16", 4095.0, 40), ("uint16", 65535.0, 30000), ("int16", 8191.0, 500), ("uint8", 255.0, 9)])
+def test_two_independent_gaussian_ssim_statements_agree(dtype, L, amp):
+    """scipy.ndimage (separable, reflect + crop) against the written-out 11 x 11 window sums of the SSIM paper."""
+    rng = np.random.default_rng(17)
+    info = np.iinfo(dtype)
+    a = rng.integers(info.min // 2, info.max // 2, size=(37, 53)).astype(np.int64)
+    b = np.clip(a + rng.integers(-amp, amp + 1, size=a.shape), info.min, info.max)
+    a, b = a.astype(dtype), b.astype(dtype)
+    s1 = orc.ssim_gaussian_band(a, b, L)
+    s2 = orc.ssim_gaussian_band_direct(a, b, L)
+    assert abs(s1 - s2) <= 1e-11 * max(1.0, abs(s1)), (s1, s2)
+    assert orc.ssim_gaussian_band_direct(a, a, L) == pytest.approx(1.0, abs=1e-12)

@@ -1,6 +1,9 @@
 """Timing / A-B probe of dm_fused_bip on the bench workload (Case B cube, 1024x1024x180 BIP).
 
-DM_FUSED_DEBUG is read by the library at every launch:
+Needs the EXPERIMENT build of the library (the shipping build reads no environment variable):
+    DM_DEBUG_HOOKS=1 python image_compression_analysis_b200/csrc/build.py --force
+and afterwards `python image_compression_analysis_b200/csrc/build.py --force` to restore the shipping build.
+In that build DM_FUSED_DEBUG is read by the library at every launch:
     0 normal   1 producer skips the copies (compute only)   2 band group idle   4 pixel group idle
     8 force the generic (runtime-geometry) kernel
 Development tool; bench.py is the contract benchmark."""
