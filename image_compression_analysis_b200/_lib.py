@@ -86,6 +86,7 @@ SYMBOLS = {
     "dm_p2p_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
     "dm_p2p_close": (C.c_int, [_P]),
     "dm_p2p_free": (C.c_int, [_P]),
+    "dm_p2p_zero": (C.c_int, [_P, C.c_int64, _P]),
     "dm_p2p_push": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, _P]),
     "dm_p2p_combine": (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_int64, _P, _P, C.c_double, _P]),

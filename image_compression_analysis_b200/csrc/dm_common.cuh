@@ -93,6 +93,7 @@ int p2p_alloc(int64_t bytes, void** ptr, void* handle64);
 int p2p_open(const void* handle64, void** ptr);
 int p2p_close(void* ptr);
 int p2p_free(void* ptr);
+int p2p_zero(void* ptr, int64_t bytes, cudaStream_t s);
 int launch_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int world,
                     uint64_t flag_value, cudaStream_t s);
 int launch_p2p_combine(const void* gathered, const void* flags, int world, uint64_t need, int64_t capacity, int64_t rec0,

@@ -179,6 +179,7 @@ int dm_p2p_alloc(int64_t bytes, void** ptr, void* handle64) { return p2p_alloc(b
 int dm_p2p_open(const void* handle64, void** ptr) { return p2p_open(handle64, ptr); }
 int dm_p2p_close(void* ptr) { return p2p_close(ptr); }
 int dm_p2p_free(void* ptr) { return p2p_free(ptr); }
+int dm_p2p_zero(void* ptr, int64_t bytes, void* stream) { return p2p_zero(ptr, bytes, static_cast<cudaStream_t>(stream)); }
 
 int dm_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int32_t world,
                 uint64_t flag_value, void* stream) {

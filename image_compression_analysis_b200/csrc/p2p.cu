@@ -116,6 +116,11 @@ int p2p_open(const void* handle64, void** ptr) {
 
 int p2p_close(void* ptr) { if (ptr) DM_CUDA(cudaIpcCloseMemHandle(ptr)); return DM_OK; }
 int p2p_free(void* ptr) { if (ptr) DM_CUDA(cudaFree(ptr)); return DM_OK; }
+int p2p_zero(void* ptr, int64_t bytes, cudaStream_t s) {
+  if (!ptr || bytes < 0) return fail(DM_EARG, "dm_p2p_zero: bad arguments");
+  DM_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, s));
+  return DM_OK;
+}
 
 int launch_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int world,
                     uint64_t flag_value, cudaStream_t s) {

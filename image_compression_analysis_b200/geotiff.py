@@ -247,6 +247,10 @@ class Reader:
             out = arr[[int(i) - 1 for i in indexes]]
         return out.astype(out_dtype) if out_dtype is not None else out
 
+    def has_explicit_mask(self) -> bool:
+        """A per-dataset mask exists (.msk sidecar or internal mask directory): rasterio gives it priority over nodata."""
+        return Path(str(self._path) + ".msk").exists() or self._mask_ifd is not None
+
     def dataset_mask(self):
         """uint8 (H,W), 0/255: .msk sidecar or internal mask if present, else any band != nodata,
         else all valid (rasterio's rule)."""

@@ -40,20 +40,30 @@ class Cube:
     meta: dict
 
 
-_CUBES: "OrderedDict[Tuple[str, int, int], Cube]" = OrderedDict()
+_CUBES: "OrderedDict[Tuple[str, int, int, int], Cube]" = OrderedDict()
 _STAGING: Dict[int, torch.Tensor] = {}
+_STAGING_BUSY: Dict[int, "torch.cuda.Event"] = {}      # id(staging buffer) -> "the upload that read it has finished"
 STATS = {"reads": 0, "hits": 0}
 
 
 def clear_cache() -> None:
     _CUBES.clear()
     _STAGING.clear()
+    _STAGING_BUSY.clear()
 
 
-def _key(path) -> Tuple[str, int, int]:
+def _key(path) -> Tuple[str, int, int, int]:
+    """(path, mtime, size, CUDA device): a cube cached on one GPU is not handed to code running on another."""
     p = Path(path)
     st = os.stat(p)
-    return (str(p.resolve()), st.st_mtime_ns, st.st_size)
+    return (str(p.resolve()), st.st_mtime_ns, st.st_size, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+
+
+def _wait_staging_free(stage: torch.Tensor) -> None:
+    """Block until the upload that last read `stage` has finished -- whichever stream or device issued it."""
+    ev = _STAGING_BUSY.pop(id(stage), None)
+    if ev is not None:
+        ev.synchronize()
 
 
 def _staging(nbytes: int) -> torch.Tensor:
@@ -90,7 +100,7 @@ def load_cube(path) -> Cube:
             nbytes = int(np.prod(shape)) * np.dtype(name).itemsize
             stage = _staging(nbytes)
             # the staging buffer is reused by the next read: wait for the previous upload before overwriting it
-            torch.cuda.current_stream().synchronize()
+            _wait_staging_free(stage)
             host = stage[:nbytes].view(tdt).view(shape)
             ds.read_native(out=host.numpy().view(np.dtype(name)))
         else:
@@ -98,11 +108,14 @@ def load_cube(path) -> Cube:
             if arr.dtype == np.uint16:
                 arr = arr.view(np.int16)
             stage = _staging(arr.nbytes)
-            torch.cuda.current_stream().synchronize()
+            _wait_staging_free(stage)
             host = stage[:arr.nbytes].view(tdt).view(arr.shape)
             host.numpy()[...] = arr
         nodata, mask, meta = ds.nodata, explicit_mask(ds), ds.meta.copy()
     t = host.to(dev, non_blocking=True)
+    busy = torch.cuda.Event()
+    busy.record()
+    _STAGING_BUSY[id(stage)] = busy
     if layout == "bsq" and B >= 16 and B % 4 == 0 and np.dtype(name).itemsize == 2:
         # rasterio always de-interleaves to (B,H,W).  Many-band cubes are evaluated from (H,W,B): the one-pass
         # kernel, the register-resident SID kernel and the BIP Sobel kernel all want whole spectra together,

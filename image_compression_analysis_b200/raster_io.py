@@ -30,11 +30,32 @@ def uint8_dtype():
     return rio.uint8 if rio is not None else "uint8"
 
 
+def has_explicit_mask(ds) -> bool:
+    """Does the dataset carry a per-dataset or alpha mask?  rasterio's dataset_mask() gives such a mask priority
+    over the nodata value (run_codec.py:249, quicklooks.py:37), so it must be honoured whether or not the file
+    also has nodata.  rasterio: mask_flag_enums; built-in reader: .msk sidecar / internal mask directory."""
+    if hasattr(ds, "has_explicit_mask"):
+        return bool(ds.has_explicit_mask())
+    flags = getattr(ds, "mask_flag_enums", None)
+    if flags is not None:
+        try:
+            names = {getattr(f, "name", str(f)) for band in flags for f in band}
+            return bool(names & {"per_dataset", "alpha"})
+        except TypeError:
+            return False
+    return False
+
+
 def explicit_mask(ds) -> Optional[np.ndarray]:
-    """dataset_mask() as bool when it carries information beyond nodata (alpha band / .msk);
-    None when everything is valid.  With a nodata value the mask is derived on the GPU instead."""
+    """dataset_mask() as bool when it carries information beyond nodata (alpha band / .msk sidecar / internal
+    mask), else None.  A nodata-derived dataset mask is NOT read here: the GPU derives it from the samples.
+    A file with BOTH an explicit mask and a nodata value returns the explicit mask (it has priority in
+    rasterio); the nodata value still goes to the GPU, where the per-band nodata tests of compute_metrics
+    (run_codec.py:250-259) and of _valid_mask_from_ds (quicklooks.py:41-42) imply the nodata-derived
+    dataset mask, so ANDing the explicit mask on top reproduces the reference's masks."""
     nd = ds.nodata
-    if nd is not None and np.isfinite(nd):
+    has_nd = nd is not None and np.isfinite(nd)
+    if has_nd and not has_explicit_mask(ds):
         return None
     m = ds.dataset_mask()
     if m is None:

@@ -96,9 +96,36 @@ def evaluate_strip(ref, tst, s: Strip, img_rows: int, layout: str, want, valid=N
         if want.lmse or want.ssim_gauss:
             evaluate(full, Want(stats=False, lmse=want.lmse, ssim_gauss=want.ssim_gauss), out=P, rows=(c0, c1),
                      data_range=data_range)
+    # run_codec.py:264: `use_mask = np.any(vm)` -- a mask with NO valid pixel anywhere in the image means "use every
+    # pixel".  That is a GLOBAL condition: a strip without valid pixels says nothing, so the valid counts of all
+    # strips are added first (one extra 8-byte all-reduce, only when a mask exists at all; every rank takes part,
+    # also one whose strip is empty) and the statistics are redone unmasked on every rank when the total is zero.
+    masked = want.stats and (valid is not None or full.ref_nodata is not None or full.tst_nodata is not None)
+    if reduce and masked:
+        import torch.distributed as dist
+        tot = P.counts[0:1].clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        if int(tot.item()) == 0:
+            redo_stats_unmasked(P, core if c1 > c0 else None, point, vdev)
     if reduce:
         P.allreduce_(group)
     return P
+
+
+def redo_stats_unmasked(P, core, want, vdev=None) -> None:
+    """The reference's all-False-mask fallback (run_codec.py:264, 271-274) for one strip: drop the (empty) masked
+    statistics and evaluate them again over every pixel.  Callers that combine strips themselves (reduce=False) call
+    this on every strip once the SUM of the strips' P.counts[0] turns out to be zero."""
+    from .engine import Want, evaluate
+    P.sums.zero_()
+    P.imax.zero_()
+    if P.hist_bins:
+        P.hist.zero_()
+    if core is not None:
+        w2 = Want(stats=True, moments=want.moments, hist_bins=want.hist_bins, generic_stats=want.generic_stats)
+        evaluate(core, w2, vdev, out=P, metrics_mask=False, plane=P.planes.get("valid"))
+    P.used_mask = False
 
 
 class PipelinedCombiner:
@@ -187,6 +214,8 @@ class P2PRunCombiner:
     Set-up needs `torch.distributed` only to hand the 64-byte IPC handles around.  Anything that fails here
     raises, and the caller falls back to RunCombiner (NCCL)."""
 
+    MAX_WORLD = 16          # kMaxWorld of csrc/p2p.cu
+
     def __init__(self, run, bands: int, hist_bins: int = 0, batch: int = 8, group=None, timeout_s: float = 20.0):
         import ctypes as C
         import torch
@@ -195,6 +224,8 @@ class P2PRunCombiner:
         from .engine import Partials
         self.run, self.bands, self.hist_bins, self.batch, self.group = run, bands, hist_bins, max(1, batch), group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > self.MAX_WORLD:     # before the collective handshake: every rank sees the same world size
+            raise RuntimeError(f"P2P exchange supports up to {self.MAX_WORLD} ranks (dm_p2p_push), not {self.world}")
         self.capacity, self.words = int(run.shape[0]), int(run.shape[1])
         self.sizes = Partials.sizes(bands, hist_bins)
         assert sum(self.sizes) == self.words
@@ -254,7 +285,10 @@ class P2PRunCombiner:
         import ctypes as C
         import torch
         from ._lib import check
-        if upto <= self._next:
+        if upto < self._next:
+            raise RuntimeError(f"P2PRunCombiner: record {upto} is behind the {self._next} already exchanged -- "
+                               "call reset() (collective) before a second sweep over the same run")
+        if upto == self._next:
             return
         i0, n = self._next, upto - self._next
         ready = torch.cuda.Event()
@@ -273,15 +307,38 @@ class P2PRunCombiner:
                                          float(self.timeout_s), st))
         self._next = upto
 
-    def finish(self, upto: int) -> None:
+    def finish(self, upto: int, check: bool = False) -> None:
+        """Exchange what is left up to record `upto`; the current stream waits for it.  check=True also
+        synchronises and raises if a combine timed out, so that a sweep cannot consume an uncombined run."""
         import torch
         self._flush(upto)
         torch.cuda.current_stream().wait_stream(self.stream)
+        if check:
+            torch.cuda.current_stream().synchronize()
+            self.check_status()
 
     def check_status(self) -> None:
         """Raises if a combine gave up waiting for a peer (call after a synchronisation point)."""
         if int(self._status.item()) != 0:
             raise RuntimeError("P2P exchange: a peer's partial vectors did not arrive within the time-out")
+
+    def reset(self) -> None:
+        """Make the object reusable for another sweep over the same run: the arrival flags hold the number of
+        records delivered so far and only ever grow, so they are zeroed -- collectively, between two barriers, so
+        that no peer is still pushing the old sweep or already pushing the new one."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        self.check_status()
+        dist.barrier(group=self.group)
+        flags = (self._base + self._flags_off)
+        import ctypes as C
+        rc = self._L.dm_p2p_zero(C.c_void_p(flags), 256, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        from ._lib import check as _check
+        _check(rc)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self._next = 0
 
     def close(self) -> None:
         import torch

@@ -302,6 +302,9 @@ int dm_p2p_alloc(int64_t bytes, void** ptr, void* handle64);
 int dm_p2p_open(const void* handle64, void** ptr);
 int dm_p2p_close(void* ptr);
 int dm_p2p_free(void* ptr);
+/* zero `bytes` of an exchange buffer on `stream` (the arrival flags, between two sweeps; the caller brackets it
+ * with barriers so that no peer is pushing) */
+int dm_p2p_zero(void* ptr, int64_t bytes, void* stream);
 int dm_p2p_push(const void* src, int64_t total_words, void* const* peer_dst, void* const* peer_flag, int32_t world,
                 uint64_t flag_value, void* stream);
 int dm_p2p_combine(const void* gathered, const void* flags, int32_t world, uint64_t need, int64_t capacity,

@@ -206,3 +206,32 @@ def test_p2p_exchange_is_bit_identical_to_nccl_when_two_gpus_are_visible():
                        capture_output=True, text=True, timeout=600, env={**os.environ, "MASTER_ADDR": "127.0.0.1"})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("p2p == nccl: True; same on all ranks: True") == world
+
+
+def test_strip_path_all_false_mask_means_unmasked():
+    """run_codec.py:264 on the row-strip path: an all-False mask (globally) falls back to every pixel; a strip that
+    merely has no valid pixel of its own does not."""
+    from image_compression_analysis_b200 import finish, sharding, synth
+    from image_compression_analysis_b200.engine import Want
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_a_pair(seed=8, bands=3, height=96, width=80)
+    H = 96
+    s = sharding.strips(H, 1)[0]
+    none_valid = np.zeros((H, 80), bool)
+    P = sharding.evaluate_strip(ref, dec, s, H, "bsq", Want(stats=True), none_valid)
+    h = P.to_host()
+    _check(finish.finish_compute_metrics(1, h.sums, h.maxs), orc.compute_metrics(ref, dec, none_valid, extras=False))
+    assert int(h.sums[0, 0]) == H * 80
+    # two strips combined by hand: the upper strip has no valid pixel, the lower one has -> the mask stands
+    lower = none_valid.copy(); lower[60:, :] = True
+    tot = None
+    parts = []
+    for st in sharding.strips(H, 2):
+        Pp = sharding.evaluate_strip(sharding.cut_bsq(ref, st), sharding.cut_bsq(dec, st), st, H, "bsq", Want(stats=True),
+                                     lower[st.buf0:st.buf1], reduce=False)
+        parts.append(Pp.to_host())
+    assert int(parts[0].counts[0]) == 0 and int(parts[1].counts[0]) > 0
+    tot = parts[0]
+    tot.isum += parts[1].isum
+    tot.imax = np.maximum(tot.imax, parts[1].imax)
+    _check(finish.finish_compute_metrics(1, tot.sums, tot.maxs), orc.compute_metrics(ref, dec, lower, extras=False))
