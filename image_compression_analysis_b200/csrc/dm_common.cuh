@@ -16,6 +16,7 @@ int sm_count();                                     // SMs of the current device
 void count_launch();                                // one more kernel launched (dm_launch_count)
 bool launch_chaining();                             // dm_launch_chaining() state of this thread
 int fused_bip_variant();                            // dm_fused_bip_variant() state of this thread
+int ssim_variant();                                 // dm_ssim_variant() state of this thread
 
 #define DM_CUDA(expr)                                              \
   do {                                                             \

@@ -17,6 +17,8 @@ bool launch_chaining() { return g_chaining; }
 void set_launch_chaining(bool on) { g_chaining = on; }
 static thread_local int g_bip_variant = 0;
 int fused_bip_variant() { return g_bip_variant; }
+static thread_local int g_ssim_variant = 0;
+int ssim_variant() { return g_ssim_variant; }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -103,6 +105,12 @@ int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
   if (!p) return fail(DM_EARG, "dm_fused_bsq: null pair");
   return launch_fused_bsq(*p, plane, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
                           hist8_z, static_cast<cudaStream_t>(stream));
+}
+
+int dm_ssim_variant(int32_t v) {
+  if (v != 0 && v != 1) return fail(DM_EARG, "dm_ssim_variant: 0 (tiled kernel) or 1 (streaming kernel)");
+  dm::g_ssim_variant = v;
+  return DM_OK;
 }
 
 int dm_sobel_mag(const void* img, int32_t dtype, int64_t rows, int64_t width, double* out, void* stream) {

@@ -23,6 +23,7 @@
 // extra halo rows of the shorter tile cost more than the third CTA's overlap buys.)
 
 #include <cmath>
+#include <type_traits>
 
 #include "dm_common.cuh"
 
@@ -178,6 +179,171 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
 
 #undef DM_TAP
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming kernel (dm_ssim_variant(1); NOT the default -- measured slower, kept as an independent second
+// implementation that the parity tests check against the oracle, and as the record of the experiment).
+// Idea: no block barrier, no halo recomputation, 64 FP64 operations per pixel instead of ~130:
+//
+//   * a WARP owns a strip of 32 output columns and streams down the rows of a segment; lane = column
+//   * horizontal pass in EXACT INTEGER arithmetic on the other pipe: the window is the Gaussian quantised to
+//     31-bit fixed point (W_k, sum exactly 2^31 -- a normalised window that differs from the ideal taps by < 2^-32,
+//     far inside the 1e-6 gate; what matters for the variance terms is that all planes see the SAME window and
+//     that nothing is rounded before the products are summed).  Per input sample the lanes store three 32-bit
+//     words in a warp-private row buffer -- p = x | y << 16, x*y, (x-y)^2 -- and every output is 11 taps x
+//     4 IMAD.WIDE.U32 (sums of W x, W p, W xy, W d^2 < 2^63; W y = (W p - W x) >> 16).  int16 samples are taken
+//     in offset binary (x ^ 0x8000): variances and covariances do not see the shift, the means get it back.
+//   * one I2F.F64.U64 per plane, then the vertical pass as a SCATTER into 11 pending outputs per lane held in
+//     registers (44 accumulators; the row loop is unrolled 11 x so that every index is static): each horizontal
+//     result is used 11 times, nothing is computed twice, no shared-memory traffic in FP64
+//   * SSIM from {E x, E y, E xy, E d^2}: sigma_x^2 + sigma_y^2 = var(d) + 2 cov, so neither x^2 nor y^2 is
+//     filtered; the quotient is a MUFU.RCP64H seed + two Newton steps (no library slow-path branch)
+//   * the next rows' samples are fetched two steps ahead into registers
+// Measured (r02, tools/probe_ssim.py, tools/ubench_fp64.cu): 10980^2 x 4 scene 8.98 ms against 6.19 ms for the tiled
+// kernel; results agree to 2e-12.  Why: IMAD.WIDE issues at ~23 lane-ops/clk/SM here (ptxas also splits the 64-bit
+// accumulate into IMAD.WIDE + IADD3 + IADD3.X: 252 warp instructions per 32 pixels) while DFMA runs at 61.5 -- on
+// this chip the FP64 pipe IS the fast wide multiplier, and an exact-integer horizontal pass costs three times what
+// the rounded one does.  What carries over to the tiled kernel: the var(d) + 2 cov form and the branch-free quotient.
+struct StreamArgs {
+  const void* ref;
+  const void* tst;
+  int64_t band_stride, width, buf_rows;
+  int64_t r_lo, r_hi;                 // counted buffer rows
+  int seg_rows, strips_x;
+  int64_t nseg;
+  uint32_t w[2 * RAD + 1];            // fixed-point taps, sum 2^31
+  double wv[2 * RAD + 1];             // w[k] * 2^-62: vertical weight including the horizontal scale
+  double c1, c2;
+  double* scratch; double* sum_acc; double* cnt_acc; void* workspace;
+};
+
+constexpr int kStreamWarps = 4;
+constexpr int kStreamBuf = 48;        // words per array of a row buffer (42 used)
+
+__device__ __forceinline__ unsigned long long madw(uint32_t a, uint32_t b, unsigned long long c) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamWarps * 32, 3)
+ssim_stream_kernel(const StreamArgs g) {
+  constexpr int NT = 2 * RAD + 1;
+  constexpr uint32_t OFS = sizeof(T) == 2 && T(-1) < T(0) ? 0x8000u : 0u;      // int16 -> offset binary
+  __shared__ uint32_t rowbuf[kStreamWarps][2][3][kStreamBuf];
+  __shared__ double red[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int band = blockIdx.y;
+  const T* A = static_cast<const T*>(g.ref) + (int64_t)band * g.band_stride;
+  const T* R = static_cast<const T*>(g.tst) + (int64_t)band * g.band_stride;
+  const int64_t c_lo = RAD, c_hi = g.width - RAD;
+  double acc_s = 0.0;
+  unsigned acc_n = 0;
+  double va[NT][4];                    // pending vertical sums: slot a started at the step with phase a
+  const int64_t ntasks = g.nseg * g.strips_x;
+  for (int64_t task = (int64_t)blockIdx.x * kStreamWarps + warp; task < ntasks; task += (int64_t)gridDim.x * kStreamWarps) {
+    const int64_t seg = task / g.strips_x;
+    const int strip = (int)(task - seg * g.strips_x);
+    const int64_t r0 = g.r_lo + seg * g.seg_rows;
+    const int64_t r1 = r0 + g.seg_rows < g.r_hi ? r0 + g.seg_rows : g.r_hi;
+    const int64_t c0 = c_lo + (int64_t)strip * 32;
+    const bool col_ok = c0 + lane < c_hi;
+    const int n_in = (int)(r1 - r0) + 2 * RAD;           // input rows r0-5 .. r1+4
+    // this lane's input columns: c0-5+lane, and (lanes 0..9) c0+27+lane; clamped columns only feed dropped outputs
+    int64_t ca = c0 - RAD + lane, cb = c0 + 32 - RAD + lane;
+    ca = ca >= g.width ? g.width - 1 : ca;
+    cb = cb >= g.width ? g.width - 1 : cb;
+    const bool second = lane < 2 * RAD;
+    const T* pa = A + (r0 - RAD) * g.width;
+    const T* pr = R + (r0 - RAD) * g.width;
+    uint32_t f0[4], f1[4];               // fetched samples of the next two rows {x(ca), y(ca), x(cb), y(cb)}
+    auto fetch = [&](int s, uint32_t (&f)[4]) {
+      if (s < n_in) {
+        const T* qa = pa + (int64_t)s * g.width;
+        const T* qr = pr + (int64_t)s * g.width;
+        f[0] = (uint32_t)(uint16_t)__ldg(qa + ca); f[1] = (uint32_t)(uint16_t)__ldg(qr + ca);
+        if (second) { f[2] = (uint32_t)(uint16_t)__ldg(qa + cb); f[3] = (uint32_t)(uint16_t)__ldg(qr + cb); }
+      }
+    };
+    fetch(0, f0);
+    fetch(1, f1);
+    // one row: stage the fetched samples, horizontal pass (integer), vertical scatter with compile-time phase PH
+    auto step = [&](auto ph_tag, int s, uint32_t (&fc)[4]) {
+      constexpr int PH = decltype(ph_tag)::value;
+      uint32_t (*buf)[kStreamBuf] = rowbuf[warp][s & 1];
+      {
+        const uint32_t x = fc[0] ^ OFS, y = fc[1] ^ OFS;
+        const uint32_t d = x > y ? x - y : y - x;
+        buf[0][lane] = x | (y << 16); buf[1][lane] = x * y; buf[2][lane] = d * d;
+        if (second) {
+          const uint32_t x2 = fc[2] ^ OFS, y2 = fc[3] ^ OFS;
+          const uint32_t d2 = x2 > y2 ? x2 - y2 : y2 - x2;
+          buf[0][lane + 32] = x2 | (y2 << 16); buf[1][lane + 32] = x2 * y2; buf[2][lane + 32] = d2 * d2;
+        }
+      }
+      fetch(s + 2, fc);                  // this buffer is free again: the row after next goes into it
+      __syncwarp();
+      unsigned long long hx = 0, hp = 0, hxy = 0, hd = 0;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const uint32_t p = buf[0][lane + k], q = buf[1][lane + k], e = buf[2][lane + k];
+        const uint32_t wk = g.w[k];
+        hx = madw(p & 0xffffu, wk, hx); hp = madw(p, wk, hp); hxy = madw(q, wk, hxy); hd = madw(e, wk, hd);
+      }
+      const unsigned long long hy = (hp - hx) >> 16;
+      const double h[4] = {__ull2double_rn(hx), __ull2double_rn(hy), __ull2double_rn(hxy), __ull2double_rn(hd)};
+#pragma unroll
+      for (int a = 0; a < NT; ++a) {
+        constexpr int dummy = 0; (void)dummy;
+        const int t = (PH - a + NT) % NT;                 // tap this slot receives now (static after unrolling)
+        const double wt = g.wv[t];
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) va[a][pl] = t == 0 ? wt * h[pl] : fma(wt, h[pl], va[a][pl]);
+      }
+      if (s >= 2 * RAD && col_ok) {                       // the slot started 10 steps ago is complete
+        constexpr int a = (PH + 1) % NT;
+        const double ux1 = va[a][0], uy1 = va[a][1], uxy = va[a][2], ud2 = va[a][3];
+        const double ux = OFS ? ux1 - 32768.0 : ux1, uy = OFS ? uy1 - 32768.0 : uy1;
+        const double vxy = fma(-ux1, uy1, uxy);           // covariance (shift invariant)
+        const double dm = ux1 - uy1;
+        const double vsum = fma(2.0, vxy, fma(-dm, dm, ud2));     // var x + var y = var(x - y) + 2 cov
+        const double num = fma(2.0, ux * uy, g.c1) * fma(2.0, vxy, g.c2);
+        const double den = fma(ux, ux, fma(uy, uy, g.c1)) * (vsum + g.c2);
+        double q;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));
+        q = fma(fma(-den, q, 1.0), q, q);
+        q = fma(fma(-den, q, 1.0), q, q);
+        acc_s = fma(num, q, acc_s);
+        acc_n += 1u;
+      }
+    };
+#define DM_STEP(PH_, F_)                                                                  \
+    if (s0 + PH_ < n_in) step(std::integral_constant<int, PH_>(), s0 + PH_, F_)
+    // 11 steps per trip (static phases); two fetch buffers alternate, 11 is odd, so a second trip swaps them
+    for (int s0 = 0; s0 < n_in; s0 += 2 * NT) {
+      DM_STEP(0, f0); DM_STEP(1, f1); DM_STEP(2, f0); DM_STEP(3, f1); DM_STEP(4, f0); DM_STEP(5, f1);
+      DM_STEP(6, f0); DM_STEP(7, f1); DM_STEP(8, f0); DM_STEP(9, f1); DM_STEP(10, f0);
+      s0 += NT;
+      DM_STEP(0, f1); DM_STEP(1, f0); DM_STEP(2, f1); DM_STEP(3, f0); DM_STEP(4, f1); DM_STEP(5, f0);
+      DM_STEP(6, f1); DM_STEP(7, f0); DM_STEP(8, f1); DM_STEP(9, f0); DM_STEP(10, f1);
+      s0 -= NT;
+    }
+#undef DM_STEP
+    __syncwarp();                        // the next task's first row reuses rowbuf[warp][0]
+  }
+  acc_s = warp_sum_f64(acc_s);
+  double cnt = warp_sum_f64((double)acc_n);
+  if (lane == 0) { red[0][warp] = acc_s; red[1][warp] = cnt; }
+  __syncthreads();
+  double t[2] = {0.0, 0.0};
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < kStreamWarps; ++w) { t[0] += red[0][w]; t[1] += red[1][w]; }
+  }
+  __syncthreads();
+  double* const accs[2] = {g.sum_acc, g.cnt_acc};
+  ordered_band_sum<2>(t, g.scratch, static_cast<Workspace*>(g.workspace)->band_counter, accs, &red[0][0]);
+}
+
 }  // namespace
 
 int ssim_nblocks() { return kSsimBlocks; }
@@ -196,11 +362,46 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
   if (img_row0 + r_hi > img_rows - RAD) r_hi = img_rows - RAD - img_row0;
   if (r_hi > r_lo && (r_lo - RAD < 0 || r_hi + RAD > p.rows))
     return fail(DM_EARG, "dm_ssim_gauss: strip lacks its 5 halo rows");
+  // the window: exp(-k^2 / (2 sigma^2)) / sum, sigma 1.5, radius 5 (scipy.ndimage.gaussian_filter, truncate 3.5)
   Taps taps;
   double sum = 0.0;
   for (int k = -RAD; k <= RAD; ++k) { taps.w[k + RAD] = std::exp(-0.5 / (1.5 * 1.5) * (double)(k * k)); sum += taps.w[k + RAD]; }
   for (int k = 0; k <= 2 * RAD; ++k) taps.w[k] /= sum;
   const double c1 = (0.01 * L) * (0.01 * L), c2 = (0.03 * L) * (0.03 * L);
+  if (ssim_variant() == 1) {
+    StreamArgs g;
+    g.ref = p.ref; g.tst = p.tst; g.band_stride = p.band_stride; g.width = p.width; g.buf_rows = p.rows;
+    g.r_lo = r_lo; g.r_hi = r_hi > r_lo ? r_hi : r_lo;
+    // 31-bit fixed-point taps, symmetric, summing to exactly 2^31 (the centre tap absorbs the rounding)
+    int64_t tot = 0;
+    for (int k = 0; k <= 2 * RAD; ++k) { g.w[k] = (uint32_t)std::llround(std::ldexp(taps.w[k], 31)); tot += g.w[k]; }
+    g.w[RAD] = (uint32_t)((int64_t)g.w[RAD] + ((int64_t)1 << 31) - tot);
+    for (int k = 0; k <= 2 * RAD; ++k) g.wv[k] = std::ldexp((double)g.w[k], -62);
+    g.c1 = c1; g.c2 = c2;
+    g.scratch = scratch; g.sum_acc = sum_acc; g.cnt_acc = cnt_acc; g.workspace = workspace;
+    const int64_t ncols = p.width - 2 * RAD, nrows = g.r_hi - g.r_lo;
+    g.strips_x = ncols > 0 ? (int)((ncols + 31) / 32) : 0;
+    // blocks per band: a fixed function of the band count (the summation order must not depend on the device);
+    // 444 = 3 resident blocks on each of 148 SMs
+    int nbx = (int)(444 / p.bands);
+    nbx = nbx < 2 ? 2 : (nbx > kSsimBlocks ? kSsimBlocks : nbx);
+    // row segments: long enough that the 10 warm-up rows of a segment are small change, short enough that every
+    // warp gets a few tasks
+    int seg = 256;
+    const int64_t warps = (int64_t)nbx * kStreamWarps;
+    while (seg > 32 && (int64_t)g.strips_x * ((nrows + seg - 1) / seg) < 3 * warps) seg >>= 1;
+    g.seg_rows = seg;
+    g.nseg = nrows > 0 ? (nrows + seg - 1) / seg : 0;
+    const dim3 sgrid((unsigned)nbx, (unsigned)p.bands);
+    switch (p.dtype) {
+      case DM_U8: ssim_stream_kernel<uint8_t><<<sgrid, kStreamWarps * 32, 0, s>>>(g); break;
+      case DM_U16: ssim_stream_kernel<uint16_t><<<sgrid, kStreamWarps * 32, 0, s>>>(g); break;
+      case DM_I16: ssim_stream_kernel<int16_t><<<sgrid, kStreamWarps * 32, 0, s>>>(g); break;
+      default: return fail(DM_EARG, "dm_ssim_gauss: bad dtype");
+    }
+    DM_LAUNCH_CHECK("ssim_stream");
+    return DM_OK;
+  }
   const dim3 grid(kSsimBlocks, (unsigned)p.bands);
 #define DM_SSIM(T)                                                                                           \
   do {                                                                                                       \

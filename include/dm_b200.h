@@ -203,6 +203,11 @@ int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_
  * scratch: double[bands * 2 * dm_ssim_nblocks()], contents irrelevant; workspace as for dm_sobel_lmse.
  * The buffer must hold 5 halo rows on each side that is not an image border.  1..2048 bands. */
 int dm_ssim_nblocks(void);
+/* which Gaussian-SSIM kernel dm_ssim_gauss launches (thread-local): 0 = the shared-memory tiled all-FP64 kernel
+ * (default), 1 = the warp-streaming kernel (exact integer horizontal pass, register-resident vertical scatter):
+ * measured slower on B200 (IMAD.WIDE runs at a third of the DFMA rate), kept as an independent second
+ * implementation that the parity tests compare with the oracle. */
+int dm_ssim_variant(int32_t variant);
 int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
                   int64_t img_row0, int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc,
                   void* workspace, void* stream);

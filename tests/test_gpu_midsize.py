@@ -86,7 +86,7 @@ def test_config3_gaussian_ssim_and_err8_full_size_vs_oracle():
     got = dm.ssim_gaussian_arrays(ref, dec2, 65535.0)
     for k in want:
         assert _close(got[k], want[k]), (k, got[k], want[k])
-    assert want["ssimw_band_avg"] < 0.9
+    assert want["ssimw_band_avg"] < 0.95
     e = ql.error_max8_arrays(ref, dec, 255, 32)
     o = orc.error_max8(ref, dec, 255, 32)
     for k in ("err8_g", "err8_z", "valid"):
@@ -235,3 +235,40 @@ def test_strip_path_all_false_mask_means_unmasked():
     tot.isum += parts[1].isum
     tot.imax = np.maximum(tot.imax, parts[1].imax)
     _check(finish.finish_compute_metrics(1, tot.sums, tot.maxs), orc.compute_metrics(ref, dec, lower, extras=False))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_both_gaussian_ssim_kernels_vs_oracle(variant):
+    """dm_ssim_variant: 0 = tiled all-FP64 kernel (default), 1 = streaming kernel (integer horizontal pass in a 31-bit
+    fixed-point window, register-resident vertical scatter).  Both against the scipy oracle at a size where every warp of the
+    streaming kernel runs several tasks and both trip copies of its unrolled row loop (segments > 22 rows), with odd
+    sizes (partial last strip / segment), int16 (offset-binary path) and uint8."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200._lib import check, lib
+    from oracle import distortion_oracle as orc
+    check(lib().dm_ssim_variant(variant))
+    try:
+        rng = np.random.default_rng(90 + variant)
+        for dtype, L, amp, shape in (("uint16", 65535.0, 2500, (2, 701, 333)), ("int16", 8191.0, 120, (1, 300, 130)),
+                                     ("uint8", 255.0, 6, (3, 97, 75)), ("uint16", 4095.0, 40, (1, 11, 11)),
+                                     ("uint16", 4095.0, 40, (1, 12, 43))):
+            info = np.iinfo(dtype)
+            a = rng.integers(info.min, info.max + 1, size=shape).astype(np.int64)
+            b = np.clip(a + rng.integers(-amp, amp + 1, size=shape), info.min, info.max)
+            a, b = a.astype(dtype), b.astype(dtype)
+            want = orc.ssim_gaussian(a, b, L)
+            got = dm.ssim_gaussian_arrays(a, b, L)
+            for k in want:
+                assert _close(got[k], want[k]), (dtype, shape, k, got[k], want[k])
+        # smooth 12-in-16 data with a small error: SSIM close to 1, variances far below the means (cancellation)
+        from image_compression_analysis_b200 import synth
+        ref, dec = synth.case_a_pair(seed=12, bands=2, height=400, width=300, sigma=1.0)
+        want = orc.ssim_gaussian(ref, dec)
+        got = dm.ssim_gaussian_arrays(ref, dec)
+        for k in want:
+            assert _close(got[k], want[k]), (k, got[k], want[k])
+        # images no larger than the crop have no window: NaN like the oracle's empty mean
+        tiny = np.zeros((1, 10, 30), np.uint16)
+        assert math.isnan(dm.ssim_gaussian_arrays(tiny, tiny, 255.0)["ssimw_b1"])
+    finally:
+        lib().dm_ssim_variant(0)

@@ -17,10 +17,20 @@ def t(fn, n=6):
     for _ in range(n): fn()
     e1.record(); e1.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
+from image_compression_analysis_b200._lib import lib
 for name, B, H, W in (("caseA tile", 4, 1024, 1024), ("scene", 4, 10980, 10980)):
     pair = mk(B, H, W, 1)
-    P = Partials.allocate(B, 0, pair.ref.device, "uint16")
-    us = t(lambda: evaluate(pair, Want(stats=False, ssim_gauss=True), out=P, data_range=4095.0))
-    print(f"{name:12s} ssim_gauss {us:9.1f} us  {4*B*H*W/us/1e3:8.1f} GB/s", flush=True)
+    res = {}
+    for variant, label in ((1, "streaming"), (0, "tiled")):
+        lib().dm_ssim_variant(variant)
+        P = Partials.allocate(B, 0, pair.ref.device, "uint16")
+        us = t(lambda: evaluate(pair, Want(stats=False, ssim_gauss=True), out=P, data_range=4095.0))
+        P.zero_()
+        evaluate(pair, Want(stats=False, ssim_gauss=True), out=P, data_range=4095.0)
+        h = P.to_host()
+        res[variant] = h.ssimw_sum / h.ssimw_cnt
+        print(f"{name:12s} ssim_gauss[{label:9s}] {us:9.1f} us  {4*B*H*W/us/1e3:8.1f} GB/s   ssimw = {res[variant]}", flush=True)
+    lib().dm_ssim_variant(0)
+    print(f"{name:12s} max |streaming - tiled| / tiled = {float(abs(res[1] - res[0]).max() / abs(res[0]).max()):.3e}")
     del pair
     torch.cuda.empty_cache()
