@@ -199,6 +199,306 @@ def make_device_pairs(torch, n_pairs: int, seed: int):
     return pairs
 
 
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (configs[0], [2], [3], [4]) -- same run, same JSON line, key "configs"
+# ------------------------------------------------------------------------------------------------
+FP64_LANES_PER_CLK_SM = 64          # DFMA lanes per clock and SM (measured 61.5-62.7: profiles/r02_ubench_fp64.txt)
+
+
+def run_configs(torch, dist, world, rank, local, peak, clocks_mhz):
+    """C1 Case-A tile statistics (batched + single-pair latency), C3 Case-A tile Gaussian SSIM + ERR8 planes,
+    C4 the full 10980 x 10980 x 4 scene with every Case-A metric STRONG-scaled over the ranks by row strips,
+    C5 the 42-pair Case-B rate sweep with every Case-B metric sharded by pair.  CUDA events, max over ranks.
+    Algorithmic bytes as SURVEY.md 8d: 4 B per sample pair, the pair counted ONCE however many kernels read it."""
+    import numpy as np
+    from image_compression_analysis_b200 import _lib, finish, sharding
+    from image_compression_analysis_b200.engine import (DevicePair, Partials, PreparedCaseAAll, PreparedFused, PreparedStats,
+                                                        PreparedStatsBatch, Want, evaluate)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.dm_launch_count()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / reps), (L.dm_launch_count() - l0) // reps
+
+    fp64_peak = 148 * FP64_LANES_PER_CLK_SM * (clocks_mhz or 1965.0) * 1e6      # DFMA lane-ops per second at this clock
+
+    def roof(bytes_, ms, bound, fp64_ops=None):
+        gbps = bytes_ / (ms * 1e-3) / 1e9
+        r = {"bound": bound, "achieved": gbps, "peak": peak, "unit": UNIT, "frac": gbps / (world * peak)}
+        if fp64_ops is not None:
+            r["fp64"] = {"ops_per_launch_set": fp64_ops, "achieved_gops": fp64_ops / (ms * 1e-3) / 1e9,
+                         "peak_gops": world * fp64_peak / 1e9, "frac": fp64_ops / (ms * 1e-3) / (world * fp64_peak),
+                         "note": "FP64-pipe operations this formulation needs (DFMA = 1) against 148 SMs x 64 lanes x the sampled SM clock"}
+        return r
+
+    # ---- C1 / C3: Case-A tiles, 32 distinct pairs per GPU (537 MB > L2), weak scaling -----------------------
+    B, H, W, NT = 4, 1024, 1024, 32
+    tile_bytes = 4 * B * H * W
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    tiles = []
+    for i in range(NT):
+        ref = torch.randint(0, 2048, (B, H, W), device=dev, dtype=torch.int16, generator=g) * 16      # 12-in-16, < 2^15
+        tst = (ref + 16 * torch.randint(-3, 4, (B, H, W), device=dev, dtype=torch.int16, generator=g)).clamp_(0, 32767)
+        tiles.append(DevicePair(ref, tst, "uint16", "bsq", B, H, W))
+    run, outs = Partials.allocate_run(NT, B, 0, dev, "uint16")
+    batch = PreparedStatsBatch(tiles, outs)
+    batch.launch()
+    torch.cuda.synchronize()
+    h0 = outs[5].to_host()
+    chk = finish.finish_compute_metrics(_lib.DM_U16, h0.sums, h0.maxs)
+    assert int(h0.sums[0, 0]) == H * W and chk["max_abs_err"] == 48 and chk["lossless"] == 0, chk
+    ms, nl = timed(batch.launch, 20)
+    # pair by pair (one launch per tile, prepared arguments) over the same rotation
+    singles = [PreparedStats(t, o) for t, o in zip(tiles, outs)]
+
+    def one_by_one():
+        for sp in singles:
+            sp.launch()
+    ms_1, _ = timed(one_by_one, 5)
+    # latency of ONE pair: device time of an isolated launch, and host wall time call -> results on the host
+    lat_dev = []
+    for i in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(200_000)
+        a.record(); singles[i % NT].launch(); b.record(); b.synchronize()
+        lat_dev.append(a.elapsed_time(b) * 1e3)
+    lat_host = []
+    pin = torch.empty(outs[0].flat.numel(), dtype=torch.int64).pin_memory()
+    for i in range(30):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        singles[i % NT].launch()
+        pin.copy_(outs[i % NT].flat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        lat_host.append((time.perf_counter() - t0) * 1e6)
+    lat_dev.sort(); lat_host.sort()
+    out["C1_caseA_tile_stats"] = {
+        "workload": "configs[0]: Case A Sentinel-2 1024x1024x4 uint16 BSQ tile pairs, compute_metrics statistics (PSNR/MSE/MAXAE/SSIM moments/data range)",
+        "pairs_per_gpu": NT, "l2_policy": f"{NT} distinct 16.8 MB pairs rotated ({NT * tile_bytes / 1e6:.0f} MB per GPU)", "scaling": "weak",
+        "batched": {"api": "engine.PreparedStatsBatch (dm_fused_stats_batch: one launch for all pairs)", "ms_per_batch": ms,
+                    "us_per_pair": ms * 1e3 / NT, "GBps": world * NT * tile_bytes / ms / 1e6, "launches_per_batch": int(nl)},
+        "pair_by_pair": {"api": "engine.PreparedStats (one dm_fused_stats launch per pair)", "us_per_pair": ms_1 * 1e3 / NT,
+                         "GBps": world * NT * tile_bytes / ms_1 / 1e6},
+        "single_pair_latency_us": {"device_isolated_launch_median": lat_dev[len(lat_dev) // 2],
+                                   "host_call_to_result_median": lat_host[len(lat_host) // 2],
+                                   "note": "device: CUDA events around one launch behind a spin kernel; host: perf_counter around "
+                                           "launch + read-back of the partial vector into pinned memory + stream sync"},
+        "roofline": roof(world * NT * tile_bytes, ms, "hbm"),
+    }
+    # C3: Gaussian SSIM + both ERR8 planes per tile
+    Pc3 = [Partials.allocate(B, 256, dev, "uint16") for _ in range(NT)]
+    c3 = [PreparedCaseAAll(t, t, (0, H), P, 4095.0, hist_bins=0) for t, P in zip(tiles, Pc3)]
+
+    def c3_all():
+        for c in c3:
+            c.launch()
+    c3_all()
+    torch.cuda.synchronize()
+    hs = Pc3[3].to_host()
+    sw = finish.finish_ssim_gauss(hs.ssimw_sum, hs.ssimw_cnt)
+    assert int(hs.ssimw_cnt[0]) == (H - 10) * (W - 10) and -1.0 < sw["ssimw_b1"] < 1.0 and int(hs.hist8_g.sum()) == H * W, sw
+    for P in Pc3:
+        P.zero_()
+    ms3, nl3 = timed(c3_all, 5)
+    ssim_ops = 104.0 * B * H * W * NT                   # 88 filter DFMA + 16 formula per band pixel
+    out["C3_caseA_tile_ssim_err8"] = {
+        "workload": "configs[2]: Case A 1024x1024x4 tile pairs: per-band statistics + ERR8 quicklook planes at caps 255 and 32 (one pass, dm_fused_bsq) "
+                    "+ per-band Gaussian-window SSIM (dm_ssim_gauss)",
+        "pairs_per_gpu": NT, "scaling": "weak", "us_per_pair": ms3 * 1e3 / NT, "GBps": world * NT * tile_bytes / ms3 / 1e6,
+        "launches_per_pair": int(nl3) // NT, "roofline": roof(world * NT * tile_bytes, ms3, "fp64", world * ssim_ops),
+    }
+    del tiles, run, outs, batch, singles, Pc3, c3
+    torch.cuda.empty_cache()
+
+    # ---- C4: one 10980 x 10980 x 4 scene, ALL Case-A metrics, strong-scaled by row strips --------------------
+    B, H, W = 4, 10980, 10980
+    scene_bytes = 4 * B * H * W
+    # 8 halo rows (5 needed): the counted rows then start a multiple of 16 bytes into the strip for any row pitch
+    # strips start on even rows: with the scene's 21 960-byte row pitch every band of a strip buffer then starts on a
+    # 16-byte boundary, which the one-pass BSQ kernel needs
+    s = sharding.strips(H, world, halo=8, align=2)[rank]
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    rows = s.buf1 - s.buf0
+    ref = torch.randint(0, 2048, (B, rows, W), device=dev, dtype=torch.int16, generator=g) * 16
+    tst = (ref + 16 * torch.randint(-3, 4, (B, rows, W), device=dev, dtype=torch.int16, generator=g)).clamp_(0, 32767)
+    full = DevicePair(ref, tst, "uint16", "bsq", B, rows, W, img_row0=s.buf0, img_rows=H)
+    c0, c1 = s.count_range
+    core = DevicePair(ref.view(-1)[c0 * W:], tst.view(-1)[c0 * W:], "uint16", "bsq", B, c1 - c0, W, None, None, s.row0, H,
+                      band_stride=rows * W)
+    NREC = 16                                             # every repetition writes its own zeroed partial vector
+    run4, outs4 = Partials.allocate_run(NREC, B, 256, dev, "uint16")
+    prep4 = [PreparedCaseAAll(core, full, (c0, c1), P, 4095.0) for P in outs4]
+    comb = None
+    exchange4 = "none"
+    if world > 1:
+        try:
+            comb = sharding.P2PRunCombiner(run4, B, 256, batch=1, timeout_s=10.0)
+            exchange4 = "nvlink peer memory (dm_p2p_push / dm_p2p_combine), one exchange per scene"
+        except Exception as e:      # noqa: BLE001
+            print(f"[bench] rank {rank}: C4 P2P exchange unavailable ({e}); NCCL", file=sys.stderr)
+            comb = sharding.RunCombiner(run4, B, 256, batch=1)
+            exchange4 = "NCCL all-gather + dm_combine_partials, one exchange per scene"
+    state = {"i": 0}
+
+    def scene():
+        i = state["i"]
+        prep4[i].launch()
+        if comb is not None:
+            comb.done(i)
+        state["i"] = i + 1
+
+    # warm-up 3 + timed 10 = 13 records of the 16
+    for _ in range(3):
+        scene()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = L.dm_launch_count()
+    e0.record()
+    for _ in range(10):
+        scene()
+    if comb is not None:
+        comb.finish(state["i"])
+    e1.record()
+    barrier()
+    ms4 = max_over_ranks(e0.elapsed_time(e1) / 10)
+    nl4 = (L.dm_launch_count() - l0) // 10
+    if isinstance(comb, sharding.P2PRunCombiner):
+        comb.check_status()
+    # one scene at a time (exchange included, nothing overlapped): the latency a single call sees
+    lat4 = []
+    for _ in range(3):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        scene()
+        if comb is not None:
+            comb.finish(state["i"])
+        b.record()
+        barrier()
+        lat4.append(max_over_ranks(a.elapsed_time(b)))
+    h4 = outs4[5].to_host()
+    torch.cuda.synchronize()
+    m4 = finish.finish_compute_metrics(_lib.DM_U16, h4.sums, h4.maxs, h4.hist, extras=True)
+    sw4 = finish.finish_ssim_gauss(h4.ssimw_sum, h4.ssimw_cnt)
+    assert int(h4.sums[0, 0]) == H * W and m4["max_abs_err"] == 48 and int(h4.hist8_g.sum()) == H * W \
+        and int(h4.ssimw_cnt[0]) == (H - 10) * (W - 10) and int(h4.hist[0:256].sum()) == H * W, (m4["max_abs_err"], sw4)
+    out["C4_scene_all_caseA_metrics"] = {
+        "workload": "configs[3]: ONE Sentinel-2 scene 10980x10980x4 uint16 BSQ, all Case-A metrics: per-band+global statistics and both ERR8 planes "
+                    "(one pass), per-band 256-bin |d| histograms, per-band Gaussian-window SSIM",
+        "scaling": "strong", "sharding": f"row strips over {world} GPU(s), 8 halo rows, partial vectors combined once per scene",
+        "exchange": exchange4, "ms_per_scene": ms4, "ms_single_scene_latency": sorted(lat4)[1], "GBps": scene_bytes / ms4 / 1e6,
+        "launches_per_scene_per_gpu": int(nl4), "pair_bytes": scene_bytes,
+        "roofline": roof(scene_bytes, ms4, "fp64", 104.0 * B * H * W),
+        "note": "time is dominated by the FP64-bound Gaussian SSIM kernel; the pair is read three times (statistics+planes, histograms, SSIM)",
+    }
+    if isinstance(comb, sharding.P2PRunCombiner):
+        comb.close()
+    del ref, tst, full, core, run4, outs4, prep4, comb
+    torch.cuda.empty_cache()
+
+    # ---- C5: Case-B rate sweep, 14 rates x 3 reps = 42 decoded cubes against ONE original, all Case-B metrics ---
+    Bb, Hb, Wb, NP = 180, 1024, 1024, 42
+    pair_bytes = 4 * Bb * Hb * Wb
+    mine = list(range(rank, NP, world))
+    g = torch.Generator(device=dev).manual_seed(11)      # the same original on every rank
+    orig = torch.randint(0, 2500, (Hb, Wb, Bb), device=dev, dtype=torch.int16, generator=g) * 4
+    decs = {}
+    for i in mine:                                        # noise amplitude grows with the "rate" index, reps differ by seed
+        gi = torch.Generator(device=dev).manual_seed(1000 + i)
+        a = 1 + (i // 3)
+        decs[i] = (orig + torch.randint(-a, a + 1, (Hb, Wb, Bb), device=dev, dtype=torch.int16, generator=gi)).clamp_(0, 32767)
+    run5, outs5 = Partials.allocate_run(NP, Bb, 0, dev, "uint16")
+    pairs5 = {i: DevicePair(orig, decs[i], "uint16", "bip", Bb, Hb, Wb) for i in mine}
+    fused5 = {i: PreparedFused(pairs5[i], Want(stats=True, sam=True), outs5[i]) for i in mine}
+    rest = Want(stats=False, sid=True, lmse=True)
+    comb5 = None
+    exchange5 = "none"
+    if world > 1:
+        try:
+            comb5 = sharding.P2PRunCombiner(run5, Bb, 0, batch=NP, timeout_s=20.0)
+            exchange5 = "nvlink peer memory, ONE exchange of the 42 partial vectors at the end of the sweep"
+        except Exception as e:      # noqa: BLE001
+            print(f"[bench] rank {rank}: C5 P2P exchange unavailable ({e}); NCCL", file=sys.stderr)
+            exchange5 = "NCCL all-reduce of the run at the end of the sweep"
+
+    def sweep():
+        run5.zero_()
+        for i in mine:
+            fused5[i].launch(chain=False)
+            evaluate(pairs5[i], rest, out=outs5[i])
+
+    def sweep_and_exchange():
+        sweep()
+        if comb5 is not None:
+            comb5.finish(NP)
+        elif world > 1:
+            # every pair was evaluated by exactly one rank and the other ranks' vectors are all-zero bits, so an int64
+            # SUM over the whole run gathers sums, maxima and (bit patterns of) float sums alike
+            dist.all_reduce(run5, op=dist.ReduceOp.SUM)
+
+    sweep_and_exchange()
+    barrier()
+    if comb5 is not None:
+        comb5.check_status()
+    h5 = outs5[NP - 1].to_host()
+    m5 = finish.finish_compute_metrics(_lib.DM_U16, h5.sums, h5.maxs)
+    s5 = finish.finish_spectral(float(h5.spec[0]), float(h5.spec[1]), float(h5.spec[2]), h5.lmse, Hb * Wb)
+    assert int(h5.sums[0, 0]) == Hb * Wb and m5["max_abs_err"] == 1 + (NP - 1) // 3 and s5["sid"] > 0 and s5["lmse"] > 0 \
+        and 0 < s5["sam_deg"] < 5, (m5["max_abs_err"], s5)
+    times5 = []
+    nl5 = 0
+    for _ in range(3):
+        if comb5 is not None:
+            comb5.reset()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = L.dm_launch_count()
+        a.record()
+        sweep_and_exchange()
+        b.record()
+        barrier()
+        times5.append(max_over_ranks(a.elapsed_time(b)))
+        nl5 = L.dm_launch_count() - l0
+    ms5 = sorted(times5)[1]
+    sid_lmse_ops = (15.0 + 20.0) * Bb * Hb * Wb * NP
+    out["C5_caseB_sweep_all_metrics"] = {
+        "workload": "configs[4]: Case B rate sweep, 14 rates x 3 reps = 42 decoded 1024x1024x180 uint16 BIP cubes against one original, all Case-B metrics: "
+                    "compute_metrics + SAM (one pass, dm_fused_bip), SID (dm_spectral), Sobel-LMSE (dm_sobel_lmse)",
+        "scaling": "strong", "sharding": f"by pair over {world} GPU(s) ({len(mine)} pairs on rank 0), results gathered once", "exchange": exchange5,
+        "ms_per_sweep": ms5, "ms_per_pair_per_gpu": ms5 / max(1, len(mine)), "GBps": NP * pair_bytes / ms5 / 1e6,
+        "launches_per_sweep_rank0": int(nl5), "pair_bytes": pair_bytes,
+        "roofline": roof(NP * pair_bytes, ms5, "fp64", sid_lmse_ops),
+        "note": "each pair is read three times (statistics+SAM at HBM speed, then the issue/FP64-bound SID and Sobel-LMSE kernels); "
+                "42 pairs on 8 ranks cannot scale past 42/6 = 7x",
+    }
+    if comb5 is not None:
+        comb5.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,6 +507,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (key \"configs\")")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -372,11 +673,13 @@ def main():
 
         from image_compression_analysis_b200.engine import evaluate_host_pairs
 
-        def e2e_run(n):
+        def e2e_run(n, share_ref=False):
             """n pairs from pinned host memory through the public sweep API: every pair is uploaded, evaluated
-            (+ exchanged across ranks), read back and finished on the host; uploads of the next pair overlap."""
+            (+ exchanged across ranks), read back and finished on the host; uploads of the next pair overlap.
+            share_ref: the pairs of a rate sweep share ONE original (BASELINE configs[4]); it is uploaded once."""
             outs_, hp_ = [], None
-            for hp_ in evaluate_host_pairs((host[i % 2] for i in range(n)), want, layout="bip"):
+            src = (host[0] for i in range(n)) if share_ref else (host[i % 2] for i in range(n))
+            for hp_ in evaluate_host_pairs(src, want, layout="bip", share_ref=share_ref):
                 o = finish.finish_compute_metrics(_lib.DM_U16, hp_.sums, hp_.maxs)
                 o.update(finish.finish_spectral(float(hp_.spec[0]), float(hp_.spec[1]), float(hp_.spec[2]), None, 1))
                 outs_.append(o)
@@ -402,13 +705,38 @@ def main():
                "ms_per_step": ms_e2e / e2e_steps,
                "api": "engine.evaluate_host_pairs(pinned host cubes) [upload of pair i+1 overlaps the kernels, exchange, "
                       "read-back and host finish of pair i] -> finish.*", "host_numa_node": numa_node}
+        # the same sweep when the decoded cubes share ONE original, as the pairs of a rate sweep do (run_codec.py:472-475):
+        # the original is uploaded once, only the decoded cube crosses the link per step
+        e2e_run(2, share_ref=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        results, hp = e2e_run(e2e_steps, share_ref=True)
+        b.record()
+        barrier()
+        assert len(results) == e2e_steps and results[-1]["max_abs_err"] == 3
+        ts = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_sh = float(ts.item())
+        e2e["shared_original"] = {"value": world * PAIR_BYTES * e2e_steps / (ms_sh * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_sh / e2e_steps,
+                                  "h2d_bytes_per_step": PAIR_BYTES // 2, "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                                  "note": "engine.evaluate_host_pairs(share_ref=True): GB/s still counts both cubes of every pair (SURVEY 8d); "
+                                          "the original is uploaded once per sweep (its one-off upload is inside the timed region)"}
+
+    peak, peak_src = hbm_peak()
+    configs = None
+    if not args.no_configs:
+        # free the headline arm's cubes first (the sweep of config 5 alone holds 16 GB at one GPU)
+        del pairs, prepared, scratch
+        torch.cuda.empty_cache()
+        configs = run_configs(torch, dist, world, rank, local, peak, clocks.get("sm_mhz") if rank == 0 else None)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = hbm_peak()
     dominant = "dm_fused_bip"
     # the step IS one launch of this kernel, back to back on one stream: its average duration over the
     # timed region is the region's CUDA-event time / launches (this rank's own clock); the isolated
@@ -446,6 +774,7 @@ def main():
                              "isolated_launch_ms: events around single launches queued behind a spin kernel (includes "
                              "the kernel's ramp-up and tail on an otherwise idle GPU)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "configs": configs,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(rows=512, reps=3)

@@ -62,6 +62,7 @@ SYMBOLS = {
     "dm_fused_bip_variant": (C.c_int, [C.c_int32]),
     "dm_validity": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P]),
     "dm_fused_stats": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_int32, C.c_uint32, _P, _P, _P, _P]),
+    "dm_fused_stats_batch": (C.c_int, [C.POINTER(DmPair), _P, C.c_int32, C.c_uint32, _P]),
     "dm_workspace_bytes": (C.c_int64, []),
     "dm_spectral": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                               C.c_int32, C.c_int32, _P, _P, _P]),

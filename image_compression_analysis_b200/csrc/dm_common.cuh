@@ -49,6 +49,8 @@ struct Workspace {
 // launchers implemented in the kernel translation units
 int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, int hist_bins,
                        uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, cudaStream_t s);
+int launch_fused_stats_batch(const dm_pair_t& p, const dm_batch_item_t* items_dev, int n_items, uint32_t flags,
+                             cudaStream_t s);
 int launch_validity(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out,
                     int64_t* counts, cudaStream_t s);
 int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_out,

@@ -79,6 +79,12 @@ int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, 
                             static_cast<cudaStream_t>(stream));
 }
 
+int dm_fused_stats_batch(const dm_pair_t* geom, const dm_batch_item_t* items_dev, int32_t n_items, uint32_t flags,
+                         void* stream) {
+  if (!geom) return fail(DM_EARG, "dm_fused_stats_batch: null geometry");
+  return launch_fused_stats_batch(*geom, items_dev, n_items, flags, static_cast<cudaStream_t>(stream));
+}
+
 int64_t dm_workspace_bytes(void) { return (int64_t)sizeof(Workspace); }
 
 int dm_spectral(const dm_pair_t* p, const uint8_t* plane, uint16_t* errmax_out, const uint8_t* lut_g,

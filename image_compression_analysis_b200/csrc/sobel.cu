@@ -2,8 +2,8 @@
 //
 // Replaces sobel_mag + mse in the LMSE loop of compute_sam_sid_lmse_caseB
 // (/root/reference/tools/run_codec.py:123-137, 341-346).  gx, gy are exact integers
-// (|g| <= 4*65535), gx^2+gy^2 < 2^38 is exact in float64 and the square root is faithfully rounded
-// (sobel_mag2), so every per-pixel term equals the reference's to the last bit or two; the order of the
+// (|g| <= 4*65535), gx^2+gy^2 < 2^38 is exact in float64; a term is evaluated with one square root and no
+// cancellation (lmse_term: ~1e-12 relative, all terms >= 0; the gate is 1e-6 on the band's sum); the order of the
 // final float64 sum differs (block-ordered partials, added in a fixed order by the blocks that finish last and
 // accumulated into the caller's per-band sums: no follow-up reduction kernel).
 //
@@ -25,27 +25,33 @@ constexpr int kSobGroups = (kSobBlocks + kSobGroup - 1) / kSobGroup;
 static_assert(kSobGroups <= kMaxGroups, "Workspace::group_counter too small");
 constexpr int TW = 32, TH = 32;
 
-// |grad| = sqrt(gx^2 + gy^2) for integer gradients (|g| <= 4*65535).  The sum of squares is an exact
-// float64 (< 2^38).  The square root is a BRANCH-FREE Goldschmidt iteration from the float32 MUFU.RSQ seed
-// (two coupled steps, then Markstein's final fma correction with the exact residual): faithfully rounded
-// (observed identical to __dsqrt_rn), and -- unlike the library routine, whose slow-path branch fences
-// every call -- the eight independent roots a thread needs per step interleave in the FP64 pipe.
-// The kernel is issue bound (ncu: 105 instructions per sample pair before this form, FP64 pipe 48 %), so
-// the helper is written for instruction count: native int->double conversions, the bare MUFU.RSQ.
-__device__ __forceinline__ double sobel_mag2(int gx, int gy) {
-  const double fx = (double)gx, fy = (double)gy;             // exact (I2F.F64: ncu shows the conversion unit at 25 %)
-  const double s = fma(fx, fx, fy * fy);
-  const float gxf = (float)gx, gyf = (float)gy;              // exact (|g| < 2^24); the seed needs ~20 bits only
-  float yf;
-  // s == 0: the clamp keeps the seed finite, g = s * y = 0 and every later step stays 0 (no select needed)
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(fmaxf(fmaf(gxf, gxf, gyf * gyf), 1e-30f)));
-  const double y = (double)yf;
-  double g = s * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  return fma(fma(-g, g, s), h, g);
+// One LMSE term (|grad a| - |grad r|)^2 from the four integer gradients (|g| <= 4*65535), with ONE square root
+// and no cancellation:   with ga = gxa^2 + gya^2, gr = gxr^2 + gyr^2 (exact float64 integers < 2^38)
+//     (sqrt ga - sqrt gr)^2 = (ga - gr)^2 / (sqrt ga + sqrt gr)^2 = (ga - gr)^2 / (ga + gr + 2 sqrt(ga gr)).
+// ga - gr is exact, the denominator is a sum of non-negative terms, so the quotient is good to the accuracy of
+// sqrt(ga gr) and of the reciprocal -- MUFU.RSQ64H / MUFU.RCP64H seeds (2^-20, tools/ubench_fp64.cu) + one Newton step
+// each: ~1e-12 relative, and every term is >= 0, so that is also the relative error of the band's sum (gate 1e-6).
+// The reference's two correctly rounded roots (run_codec.py:137, 344) cost twice the FP64-pipe slots, and the
+// kernel is issue bound: 20 FP64 operations + 2 MUFU per sample pair here against 40 + conversions before.  The
+// integers enter float64 through the 2^52 mantissa splice (one exact subtraction; an I2F.F64 costs two pipe slots).
+// 1e-30 is added to both sums of squares: it vanishes next to any non-zero sum and keeps 0/0 out of flat areas
+// (ga = gr = 0 gives exactly 0).
+__device__ __forceinline__ double splice_s32(int g) {          // exact for |g| < 2^20
+  return __hiloint2double(0x43300000, g + (1 << 20)) - (4503599627370496.0 + 1048576.0);
+}
+__device__ __forceinline__ double lmse_term(int gxa, int gya, int gxr, int gyr) {
+  const double fxa = splice_s32(gxa), fya = splice_s32(gya), fxr = splice_s32(gxr), fyr = splice_s32(gyr);
+  const double ga = fma(fxa, fxa, fma(fya, fya, 1e-30));
+  const double gr = fma(fxr, fxr, fma(fyr, fyr, 1e-30));
+  const double dg = ga - gr, p = ga * gr;
+  double y, q;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  double sq = p * y;                                            // ~ sqrt(ga gr)
+  sq = fma(fma(-sq, sq, p), 0.5 * y, sq);                       // one Newton step
+  const double den = fma(2.0, sq, ga + gr);
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));
+  q = fma(fma(-den, q, 1.0), q, q);
+  return (dg * dg) * q;
 }
 
 template <typename T>
@@ -89,20 +95,17 @@ sobel_lmse_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
       const int lr = ty + j;
       if (r0 + lr < row_end && c0 + tx < width) {
         const int (*s)[TW + 3] = sa;
-        double mag[2];
+        int gx[2], gy[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int p00 = s[lr][tx], p01 = s[lr][tx + 1], p02 = s[lr][tx + 2];
           const int p10 = s[lr + 1][tx], p12 = s[lr + 1][tx + 2];
           const int p20 = s[lr + 2][tx], p21 = s[lr + 2][tx + 1], p22 = s[lr + 2][tx + 2];
-          const int gx = (p00 - p02) + 2 * (p10 - p12) + (p20 - p22);      // |g| <= 4*65535: int32
-          const int gy = (p00 - p20) + 2 * (p01 - p21) + (p02 - p22);
-          const double fx = (double)gx, fy = (double)gy;                   // exact; fx^2 + fy^2 < 2^38 exact
-          mag[q] = __dsqrt_rn(fma(fx, fx, fy * fy));
+          gx[q] = (p00 - p02) + 2 * (p10 - p12) + (p20 - p22);             // |g| <= 4*65535: int32
+          gy[q] = (p00 - p20) + 2 * (p01 - p21) + (p02 - p22);
           s = sr;
         }
-        const double e = __dsub_rn(mag[0], mag[1]);
-        acc += __dmul_rn(e, e);
+        acc += lmse_term(gx[0], gy[0], gx[1], gy[1]);
       }
     }
   }
@@ -177,10 +180,9 @@ sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restri
         for (int o = 0; o < 2; ++o) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const double ma = sobel_mag2(aL.v[o][h] - aR.v[o][h], aL.d[o][h] + 2 * aC.d[o][h] + aR.d[o][h]);
-            const double mr = sobel_mag2(rL.v[o][h] - rR.v[o][h], rL.d[o][h] + 2 * rC.d[o][h] + rR.d[o][h]);
-            const double e = __dsub_rn(ma, mr);
-            const double t = (live && (o == 0 || two)) ? __dmul_rn(e, e) : 0.0;   // column past the item / row past the strip
+            const double term = lmse_term(aL.v[o][h] - aR.v[o][h], aL.d[o][h] + 2 * aC.d[o][h] + aR.d[o][h],
+                                          rL.v[o][h] - rR.v[o][h], rL.d[o][h] + 2 * rC.d[o][h] + rR.d[o][h]);
+            const double t = (live && (o == 0 || two)) ? term : 0.0;          // column past the item / row past the strip
             if (h == 0) acc0 += t; else acc1 += t;
           }
         }

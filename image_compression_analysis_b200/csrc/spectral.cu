@@ -276,6 +276,7 @@ template <int DT, int NWL>
 __global__ void __launch_bounds__(kSpecThreads)
 spectral_warp_bip16(SpecArgs g) {
   __shared__ double red[3][kSpecThreads / 32];
+  __shared__ int2 slow_list[kSpecThreads / 32][2 * NWL * 32];       // SID: (a', r') of the samples that need log()
   const uint32_t* ref = static_cast<const uint32_t*>(g.ref);
   const uint32_t* tst = static_cast<const uint32_t*>(g.tst);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -330,37 +331,79 @@ spectral_warp_bip16(SpecArgs g) {
       }
     }
     if (g.want_sid) {
-      // Ap = (a - amin + 1e-12) / sum_b(a - amin + 1e-12); the integer part of the sum is exact
-      const double SA = (double)((long long)sa - (long long)B * amin) + (double)B * 1e-12;
-      const double SR = (double)((long long)sr - (long long)B * rmin) + (double)B * 1e-12;
-      const double iSA = 1.0 / SA, iSR = 1.0 / SR;
-      const double eA = 1e-12 * iSA, eR = 1e-12 * iSR;
+      // SID from ONE exact numerator per sample.  With a' = a - amin, r' = r - rmin (integers >= 0), eps = 1e-12,
+      // SA = sum a' + B eps, SR = sum r' + B eps (the integer parts exact), the reference's (run_codec.py:334-339)
+      //   Ap - Rp = n / (SA SR),   n = (a' + eps) SR - (r' + eps) SA
+      //   (Ap + 1e-15) / (Rp + 1e-15) = (1 + z) / (1 - z),   z = n / D,   D = (a'+eps) SR + (r'+eps) SA + 2e-15 SA SR
+      // so the term (Ap - Rp) ln(..) = n * 2 atanh(z) / (SA SR): two fused multiply-adds give n and D straight from the
+      // integer samples (a' SR and r' SA are exact products < 2^53 up to the eps parts, so the cancellation in n
+      // costs nothing -- this is where the float64 quotients Ap, Rp of the reference lose their digits, not here),
+      // 1/D is a MUFU.RCP64H seed + two Newton steps, atanh is six odd terms (|z| < 0.12: next term < 7e-13).  Every
+      // term is >= 0, so a relative error of 1e-12 per term is 1e-12 on the sum.  15 FP64 operations and no
+      // conversion-unit instruction per sample (was ~30 + 3); 1 / (SA SR) is applied once per pixel.  |z| >= 0.12
+      // (the bands where a spectrum has its minimum, large relative errors) takes the reference's own expression
+      // with log() behind a warp-uniform guard.
+      const double SAi = (double)((long long)sa - (long long)B * amin), SRi = (double)((long long)sr - (long long)B * rmin);
+      const double SA = SAi + (double)B * 1e-12, SR = SRi + (double)B * 1e-12;
+      const double cE = -1e-12 * (SR - SA);                            // P2 = r' SA + cE
+      const double cD = 2.0 * SR * fma(1e-15, SA, 1e-12);              // D = a' SR + P2 + cD
       double t = 0.0;
-      unsigned slow_mask = 0;                                 // bit 2j+h: this lane's sample needs log()
+      unsigned slow_mask = 0;                                          // bit 2j+h: this lane's sample needs log()
 #pragma unroll
       for (int j = 0; j < NWL; ++j) {
         const bool have = lane + 32 * j < WPX;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int a = sample16<DT>(x[j], h) - amin, r = sample16<DT>(y[j], h) - rmin;
-          bool slow;
-          const double term = sid_term_fast(fma((double)a, iSA, eA), fma((double)r, iSR, eR), &slow);
-          t += (have && !slow) ? term : 0.0;
+          // int -> float64 by splicing the non-negative integer into the mantissa of 2^52 (one exact subtraction;
+          // the conversion instruction costs two FP64-pipe slots, tools/ubench_fp64.cu)
+          const double ad = __hiloint2double(0x43300000, sample16<DT>(x[j], h) - amin) - 4503599627370496.0;
+          const double rd = __hiloint2double(0x43300000, sample16<DT>(y[j], h) - rmin) - 4503599627370496.0;
+          const double p2 = fma(rd, SA, cE);
+          const double n = fma(ad, SR, -p2);
+          const double D = fma(ad, SR, p2) + cD;
+          double q;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(D));
+          q = fma(fma(-D, q, kAtanhC[5]), q, q);
+          q = fma(fma(-D, q, kAtanhC[5]), q, q);
+          const double z = n * q, z2 = z * z;
+          const bool slow = __double2hiint(z2) >= 0x3f8d7dbf;         // z^2 >= 0.0144 (high word of 0.0144), i.e. |z| >= 0.12
+          double pz = kAtanhC[0];                                      // 1/11: six odd terms, next one < 0.12^12 / 13 = 7e-13
+          pz = fma(pz, z2, kAtanhC[1]);
+          pz = fma(pz, z2, kAtanhC[2]);
+          pz = fma(pz, z2, kAtanhC[3]);
+          pz = fma(pz, z2, kAtanhC[4]);
+          pz = fma(pz, z2, kAtanhC[5]);
+          t = fma(n, (have && !slow) ? z * pz : 0.0, t);
           slow_mask |= (have && slow) ? (1u << (2 * j + h)) : 0u;
         }
       }
+      t *= 2.0 / (SA * SR);
       if (__any_sync(0xffffffffu, slow_mask != 0)) {
+        // The samples that need log() -- typically one or two per pixel (the band of the minimum when the two spectra
+        // have it in different places, dark bands with a large relative error), scattered over lanes and register
+        // slots -- are COMPACTED through a warp-private list and evaluated side by side, one per lane: one pass
+        // through the library code per pixel instead of one per occupied register slot (up to 2 NWL).
+        int2* list = slow_list[warp];
+        int base = 0;
 #pragma unroll
         for (int j = 0; j < NWL; ++j) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            if (slow_mask & (1u << (2 * j + h))) {
-              const int a = sample16<DT>(x[j], h) - amin, r = sample16<DT>(y[j], h) - rmin;
-              const double ap = fma((double)a, iSA, eA), rp = fma((double)r, iSR, eR);
-              t += (ap - rp) * log((ap + 1e-15) / (rp + 1e-15));
-            }
+            const bool mine = (slow_mask >> (2 * j + h)) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, mine);
+            if (mine) list[base + __popc(b & ((1u << lane) - 1u))] = make_int2(sample16<DT>(x[j], h) - amin, sample16<DT>(y[j], h) - rmin);
+            base += __popc(b);
           }
         }
+        __syncwarp();
+        const double iSA = 1.0 / SA, iSR = 1.0 / SR;
+        const double eA = 1e-12 * iSA, eR = 1e-12 * iSR;
+        for (int i = lane; i < base; i += 32) {
+          const int2 v = list[i];
+          const double ap = fma((double)v.x, iSA, eA), rp = fma((double)v.y, iSR, eR);      // run_codec.py:334-337
+          t += (ap - rp) * log((ap + 1e-15) / (rp + 1e-15));                                   // :338-339
+        }
+        __syncwarp();
       }
       s_sid += t;
     }

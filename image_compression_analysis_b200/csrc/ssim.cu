@@ -57,6 +57,8 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
   const T* A = ref + (int64_t)band * band_stride;
   const T* R = tst + (int64_t)band * band_stride;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  constexpr uint32_t OFS = sizeof(T) == 2 && T(-1) < T(0) ? 0x8000u : 0u;      // int16 -> offset binary
+  constexpr double kSplice = 4503599627370496.0 + (OFS ? 32768.0 : 0.0);       // 2^52 (+ the int16 offset)
   const int64_t c_lo = RAD, c_hi = width - RAD;        // counted columns [c_lo, c_hi)
   const int64_t ncols = c_hi - c_lo, nrows = r_hi - r_lo;
   double acc = 0.0, cnt = 0.0;
@@ -99,9 +101,10 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
         const int e = threadIdx.x + 256 * k;
         if (e < IH * IW) {
           const int lr = e / IW, lc = e - lr * IW;
-          // (T)(...) restores the sample's sign for int16 cubes
-          xs[lr][lc] = (int)(T)(pre[k] & 0xffffu);
-          ys[lr][lc] = (int)(T)(pre[k] >> 16);
+          // samples go to shared memory in offset binary (int16: x ^ 0x8000), i.e. as non-negative integers
+          // below 2^16, which pass H turns into float64 with the 2^52 splice (see there)
+          xs[lr][lc] = (int)((pre[k] & 0xffffu) ^ OFS);
+          ys[lr][lc] = (int)((pre[k] >> 16) ^ OFS);
         }
       }
       __syncthreads();
@@ -115,7 +118,10 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
         double vx[14], vy[14], vq[14], vp[14];
 #pragma unroll
         for (int k = 0; k < 14; ++k) {
-          const double x = (double)xs[lr][g4 + k], y = (double)ys[lr][g4 + k];
+          // int -> float64 without the conversion unit (I2F.F64 costs two FP64-pipe slots here, measured): the
+          // sample spliced into the mantissa of 2^52 IS 2^52 + u; one exact subtraction gives u (or u - 32768)
+          const double x = __hiloint2double(0x43300000, xs[lr][g4 + k]) - kSplice;
+          const double y = __hiloint2double(0x43300000, ys[lr][g4 + k]) - kSplice;
           vx[k] = x; vy[k] = y; vq[k] = fma(x, x, y * y); vp[k] = x * y;
         }
 #pragma unroll
@@ -157,7 +163,13 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
             const double vsum = uq - mm, vxy = uxy - ux * uy;
             const double num = (2.0 * ux * uy + c1) * (2.0 * vxy + c2);
             const double den = (mm + c1) * (vsum + c2);
-            acc += num / den;
+            // quotient: MUFU.RCP64H seed (~2^-20) + two Newton steps (full precision), no slow-path branch;
+            // den >= c1 * c2 > 0 and far from the exponent limits
+            double q;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));
+            q = fma(fma(-den, q, 1.0), q, q);
+            q = fma(fma(-den, q, 1.0), q, q);
+            acc = fma(num, q, acc);
             cnt += 1.0;
           }
         }

@@ -42,6 +42,7 @@ struct StatsArgs {
   int64_t* sums;
   int64_t* maxs;
   int64_t* hist;
+  const dm_batch_item_t* items;   // batch launch: blockIdx.y selects {ref, tst, sums, maxs}; else null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -271,6 +272,10 @@ template <int DT, bool MASK, bool MOMENTS, bool HIST>
 __global__ void __launch_bounds__(kThreadsBsq)
 stats_bsq_packed(StatsArgs g, int64_t chunk_vecs, int64_t nchunk) {
   extern __shared__ unsigned hist_sh[];     // HIST: K*32 lane-private counters of the current band
+  if (g.items) {                             // batch launch (dm_fused_stats_batch): this block row's pair
+    const dm_batch_item_t it = g.items[blockIdx.y];
+    g.ref = it.ref; g.tst = it.tst; g.sums = it.sums; g.maxs = it.maxs;
+  }
   const int tid = threadIdx.x, lane = tid & 31;
   const int K = g.hist_bins;
   constexpr int EB = DT == DM_U8 ? 1 : 2;   // bytes per sample
@@ -663,7 +668,7 @@ int blocks_per_sm(KernelT kernel, int threads, size_t smem) {
 }
 
 template <int DT, bool MASK, bool MOMENTS, bool HIST>
-int run_bsq(const StatsArgs& g, cudaStream_t s) {
+int run_bsq(const StatsArgs& g, cudaStream_t s, int n_items = 1) {
   auto kernel = stats_bsq_packed<DT, MASK, MOMENTS, HIST>;
   const size_t smem = HIST ? (size_t)g.hist_bins * 32 * sizeof(unsigned) : 0;
   if (smem > 48 * 1024)
@@ -675,14 +680,16 @@ int run_bsq(const StatsArgs& g, cudaStream_t s) {
   // a chunk is 1..8 trips of the unrolled inner loop (<= 128 packed words per accumulator between
   // spills); small cubes get small chunks so that every SM has work
   const int64_t trip = (int64_t)kThreadsBsq * kUnrollBsq;
-  int64_t trips = (g.bands * nvec + max_blocks * trip - 1) / (max_blocks * trip);
+  int64_t trips = (g.bands * nvec * n_items + max_blocks * trip - 1) / (max_blocks * trip);
   trips = trips < 1 ? 1 : (trips > 8 ? 8 : trips);
   const int64_t chunk_vecs = trips * trip;
   int64_t nchunk = (nvec + chunk_vecs - 1) / chunk_vecs;
   if (nchunk < 1) nchunk = 1;
   const int64_t units = g.bands * nchunk;
-  const int64_t grid = units < max_blocks ? units : max_blocks;
-  kernel<<<(unsigned)grid, kThreadsBsq, smem, s>>>(g, chunk_vecs, nchunk);
+  int64_t per_item = max_blocks / n_items;              // a batch shares the resident blocks between its pairs
+  if (per_item < 1) per_item = 1;
+  const int64_t grid = units < per_item ? units : per_item;
+  kernel<<<dim3((unsigned)grid, (unsigned)n_items), kThreadsBsq, smem, s>>>(g, chunk_vecs, nchunk);
   DM_LAUNCH_CHECK("stats_bsq_packed");
   return DM_OK;
 }
@@ -771,7 +778,7 @@ int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, 
   if (plane) { int b = plane_bit; while (b < 128) { b <<= 1; ++g.plane_shift; } }
   g.bands = p.bands; g.npix = p.rows * p.width;
   g.band_stride = bip ? 1 : p.band_stride;
-  g.hist_bins = hist_bins; g.sums = sums; g.maxs = maxs; g.hist = hist;
+  g.hist_bins = hist_bins; g.sums = sums; g.maxs = maxs; g.hist = hist; g.items = nullptr;
   if (g.npix == 0) return DM_OK;
   if (!bip && p.band_stride < g.npix) return fail(DM_EARG, "dm_fused_stats: band_stride < rows*width");
   const bool moments = !(flags & DM_STATS_NO_MOMENTS);
@@ -806,6 +813,31 @@ int launch_fused_stats(const dm_pair_t& p, const uint8_t* plane, int plane_bit, 
     case DM_U16: return dispatch_mask<DM_U16>(g, bip_cols, moments, s);
     default: return dispatch_mask<DM_I16>(g, bip_cols, moments, s);
   }
+}
+
+int launch_fused_stats_batch(const dm_pair_t& p, const dm_batch_item_t* items_dev, int n_items, uint32_t flags,
+                             cudaStream_t s) {
+  if (!items_dev || n_items < 0) return fail(DM_EARG, "dm_fused_stats_batch: null items / negative count");
+  if (n_items > 65535) return fail(DM_EARG, "dm_fused_stats_batch: at most 65535 pairs per launch");
+  if (p.layout != DM_BSQ) return fail(DM_EUNSUPPORTED, "dm_fused_stats_batch: DM_BSQ cubes only");
+  if (p.dtype != DM_U8 && p.dtype != DM_U16 && p.dtype != DM_I16) return fail(DM_EARG, "dm_fused_stats_batch: bad dtype");
+  if (p.bands <= 0 || p.rows < 0 || p.width < 0) return fail(DM_EARG, "dm_fused_stats_batch: bad geometry");
+  if (p.band_stride < p.rows * p.width) return fail(DM_EARG, "dm_fused_stats_batch: band_stride < rows*width");
+  if ((p.band_stride * elem_bytes(p.dtype)) % 16) return fail(DM_EUNSUPPORTED, "dm_fused_stats_batch: bands must start on 16-byte boundaries");
+  if (flags & DM_STATS_GENERIC) return fail(DM_EUNSUPPORTED, "dm_fused_stats_batch: packed kernel only");
+  StatsArgs g;
+  g.ref = nullptr; g.tst = nullptr; g.plane = nullptr; g.plane_bit = 0; g.plane_shift = 0;
+  g.bands = p.bands; g.npix = p.rows * p.width; g.band_stride = p.band_stride;
+  g.hist_bins = 0; g.sums = nullptr; g.maxs = nullptr; g.hist = nullptr; g.items = items_dev;
+  if (g.npix == 0 || n_items == 0) return DM_OK;
+  const bool moments = !(flags & DM_STATS_NO_MOMENTS);
+#define DM_BATCH(DT) (moments ? run_bsq<DT, false, true, false>(g, s, n_items) : run_bsq<DT, false, false, false>(g, s, n_items))
+  switch (p.dtype) {
+    case DM_U8: return DM_BATCH(DM_U8);
+    case DM_U16: return DM_BATCH(DM_U16);
+    default: return DM_BATCH(DM_I16);
+  }
+#undef DM_BATCH
 }
 
 }  // namespace dm

@@ -485,6 +485,102 @@ class PreparedFused:
             check(self._fn(*self._args))
 
 
+class PreparedStats:
+    """A prepared launch of dm_fused_stats for one unmasked pair and one output vector (every ctypes argument built
+    once; `launch()` is a single foreign call).  For latency-critical single tiles: a Case-A tile's kernel is a few
+    microseconds, the per-call Python work of `evaluate` several times that."""
+
+    def __init__(self, pair: DevicePair, out: "Partials", moments: bool = True, hist_bins: int = 0):
+        if needs_plane(pair, None):
+            raise ValueError("PreparedStats covers unmasked pairs; use evaluate() for the rest")
+        if hist_bins != out.hist_bins and hist_bins:
+            raise ValueError("hist_bins must match the partial vector's")
+        self._keep = (pair, out)
+        self._cp = pair.c_pair()
+        self._fn = lib().dm_fused_stats
+        flags = 0 if moments else _lib.DM_STATS_NO_MOMENTS
+        self._args = (C.byref(self._cp), None, DM_VALID_METRICS, hist_bins, flags, _ptr(out.sums), _ptr(out.imax),
+                      _ptr(out.hist) if hist_bins else None, _stream_ptr())
+
+    def launch(self) -> None:
+        check(self._fn(*self._args))
+
+
+class PreparedCaseAAll:
+    """Every Case-A metric of one (strip of a) BSQ image, prepared once and launched without any allocation:
+    per-band statistics + both ERR8 planes in ONE pass (dm_fused_bsq), per-band |d| histograms (dm_fused_stats,
+    statistics-light variant; only its histogram is kept), Gaussian-window SSIM (dm_ssim_gauss).  Three foreign
+    calls per launch; planes, scratch and the histogram pass's throw-away statistics are owned by the object.
+
+    core   the COUNTED rows (a view of `full`'s buffers: same storage, band_stride of the buffer)
+    full   the resident rows including the halo the SSIM window needs; rows = counted rows in buffer coordinates"""
+
+    def __init__(self, core: DevicePair, full: DevicePair, rows: Tuple[int, int], out: "Partials", data_range: float,
+                 err8_caps=(255, 32), hist_bins: int = 256):
+        dev = core.ref.device
+        L = lib()
+        self._keep = (core, full, out)
+        self._cc, self._cf = core.c_pair(), full.c_pair()
+        self.planes = {"err8_g": torch.empty(core.npix, dtype=torch.uint8, device=dev),
+                       "err8_z": torch.empty(core.npix, dtype=torch.uint8, device=dev)}
+        lut_g, lut_z = _lut_on_device(err8_caps[0], dev), _lut_on_device(err8_caps[1], dev)
+        self._luts = (lut_g, lut_z)
+        st = _stream_ptr()
+        self._ws = workspace(dev)
+        self._a_bsq = (C.byref(self._cc), None, _ptr(out.sums), _ptr(out.imax), None,
+                       _ptr(lut_g), lut_g.numel() - 1, _ptr(self.planes["err8_g"]), _ptr(out.hist8_g),
+                       _ptr(lut_z), lut_z.numel() - 1, _ptr(self.planes["err8_z"]), _ptr(out.hist8_z), st)
+        self._junk = torch.zeros(2 * core.bands * DM_NSTAT, dtype=torch.int64, device=dev)
+        self._a_hist = (C.byref(self._cc), None, DM_VALID_METRICS, hist_bins, _lib.DM_STATS_NO_MOMENTS, _ptr(self._junk),
+                        _ptr(self._junk[core.bands * DM_NSTAT:]), _ptr(out.hist), st)
+        self._scr = _scratch(dev, "ssim", full.bands * L.dm_ssim_nblocks() * 2)
+        self._a_ssim = (C.byref(self._cf), float(data_range), rows[0], rows[1], full.img_row0, full.img_rows,
+                        _ptr(self._scr), _ptr(out.ssimw_sum), _ptr(out.ssimw_cnt), _ptr(self._ws), st)
+        self._hist_bins = hist_bins
+        self._L = L
+
+    def launch(self) -> None:
+        L = self._L
+        check(L.dm_fused_bsq(*self._a_bsq))
+        if self._hist_bins:
+            check(L.dm_fused_stats(*self._a_hist))
+        check(L.dm_ssim_gauss(*self._a_ssim))
+
+
+class PreparedStatsBatch:
+    """A prepared ONE-LAUNCH evaluation of the compute_metrics statistics of many pairs of one geometry (the tiles
+    of a manifest / the decoded tiles of a rate sweep; dm_fused_stats_batch).  A Case-A tile pair is 16.8 MB: 2.6 us
+    at HBM speed, less than a kernel launch, so pair-by-pair evaluation is launch bound; here all pairs share one
+    launch and the host makes one foreign call.  BSQ cubes, no mask, no histogram (evaluate() serves the rest)."""
+
+    def __init__(self, pairs, outs, moments: bool = True):
+        pairs, outs = list(pairs), list(outs)
+        if not pairs or len(pairs) != len(outs):
+            raise ValueError("PreparedStatsBatch needs as many partial vectors as pairs (at least one)")
+        p0 = pairs[0]
+        for q in pairs:
+            if (q.layout, q.np_dtype, q.bands, q.rows, q.width, q.band_stride) != (p0.layout, p0.np_dtype, p0.bands, p0.rows,
+                                                                                   p0.width, p0.band_stride):
+                raise ValueError("the pairs of a batch must share one geometry and sample type")
+            if q.layout != "bsq" or needs_plane(q, None):
+                raise ValueError("PreparedStatsBatch covers unmasked BSQ pairs; use evaluate() for the rest")
+            if (q.ref.data_ptr() | q.tst.data_ptr()) & 15:
+                raise ValueError("the cubes of a batch must be 16-byte aligned")
+        items = np.empty((len(pairs), 4), dtype=np.int64)
+        for i, (q, o) in enumerate(zip(pairs, outs)):
+            items[i] = (q.ref.data_ptr(), q.tst.data_ptr(), o.sums.data_ptr(), o.imax.data_ptr())
+        self._items = torch.from_numpy(items).to(p0.ref.device)        # dm_batch_item_t[n] on the device
+        self._cp = p0.c_pair()
+        self._keep = (pairs, outs)
+        self._n = len(pairs)
+        self._flags = 0 if moments else _lib.DM_STATS_NO_MOMENTS
+        self._fn = lib().dm_fused_stats_batch
+        torch.cuda.current_stream().synchronize()                       # the item array is resident before the first launch
+
+    def launch(self) -> None:
+        check(self._fn(C.byref(self._cp), _ptr(self._items), self._n, self._flags, _stream_ptr()))
+
+
 def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
              out: Optional[Partials] = None, rows: Optional[Tuple[int, int]] = None,
              data_range: Optional[float] = None, metrics_mask: bool = True,
@@ -586,7 +682,8 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     return P
 
 
-def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Optional[str] = None, group=None):
+def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Optional[str] = None, group=None,
+                        share_ref: bool = False):
     """Pipelined evaluation of a sweep of HOST pairs (the decoded cubes of a rate sweep): a generator that takes
     (ref, tst) pinned host tensors and yields one HostPartials per pair, in order.
 
@@ -594,7 +691,11 @@ def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Option
     ranks if any, read-back of the 31.5 KB partial vector and the host-side finish.  Done one pair at a time,
     everything after the upload leaves the link idle; here pair i+1 is uploaded on a second stream while pair
     i computes and pair i-1 is finished on the host, so the link -- the only real bound of the end-to-end
-    path -- never waits.  Results are identical to evaluate() + to_host() pair by pair."""
+    path -- never waits.  Results are identical to evaluate() + to_host() pair by pair.
+
+    share_ref=True: a rate sweep compares MANY decoded cubes with ONE original (run_codec.py:472-475 loops rates and
+    reps over the same src_path).  When consecutive items carry the same pinned original (same storage), it is
+    uploaded once and stays resident; only the decoded cube crosses the link, which halves the bytes per pair."""
     from collections import deque
     dev = require_cuda()
     comp = torch.cuda.current_stream(dev)
@@ -605,6 +706,7 @@ def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Option
     # in the loop -- a cudaMalloc for a 377 MB cube would synchronise the device in the middle of the pipeline
     slots = [None, None, None]              # [dr, dt, event "kernels that read this slot are done"]
     counter = [0]
+    shared = {"key": None, "dev": None}     # share_ref: the resident original
 
     def start_upload(item):
         ref, tst = item
@@ -615,20 +717,33 @@ def evaluate_host_pairs(pairs, want: Want, layout: str = "bip", np_dtype: Option
         k = counter[0] % 3
         counter[0] += 1
         slot = slots[k]
-        if slot is None or slot[0].shape != hr.shape or slot[0].dtype != hr.dtype:
-            slot = slots[k] = [torch.empty(hr.shape, dtype=hr.dtype, device=dev),
+        if slot is None or slot[1].shape != ht.shape or slot[1].dtype != ht.dtype:
+            slot = slots[k] = [None if share_ref else torch.empty(hr.shape, dtype=hr.dtype, device=dev),
                                torch.empty(ht.shape, dtype=ht.dtype, device=dev), None]
             up.wait_stream(comp)            # fresh memory may have had users on the compute stream
+        new_ref = None
+        if share_ref:
+            key = (hr.data_ptr(), tuple(hr.shape), hr.dtype)
+            if shared["key"] != key:
+                # a new original gets its own buffer, allocated on the compute stream like the slots (the previous
+                # one may still be read by queued kernels; the DevicePairs that reference it keep it alive)
+                shared["dev"], shared["key"] = torch.empty(hr.shape, dtype=hr.dtype, device=dev), key
+                up.wait_stream(comp)
+                new_ref = shared["dev"]
+        dref = shared["dev"] if share_ref else slot[0]
         with torch.cuda.stream(up):
             if slot[2] is not None:
                 up.wait_event(slot[2])      # the pair that lived here three uploads ago has been evaluated
-            slot[0].copy_(hr, non_blocking=True)
+            if new_ref is not None:
+                new_ref.copy_(hr, non_blocking=True)
+            elif not share_ref:
+                slot[0].copy_(hr, non_blocking=True)
             slot[1].copy_(ht, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(up)
         shape = tuple(hr.shape)
         B, H, W = (shape[0], shape[1], shape[2]) if layout == "bsq" else (shape[2], shape[0], shape[1])
-        return DevicePair(slot[0], slot[1], name, layout, B, H, W), ev, slot
+        return DevicePair(dref, slot[1], name, layout, B, H, W), ev, slot
 
     def finish_one(entry):
         P, host, ev = entry

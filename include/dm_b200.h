@@ -120,6 +120,22 @@ int dm_validity(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out,
 int dm_fused_stats(const dm_pair_t* p, const uint8_t* plane, int32_t plane_bit, int32_t hist_bins,
                    uint32_t flags, int64_t* sums, int64_t* maxs, int64_t* hist, void* stream);
 
+/* the same reduction for a BATCH of pairs of one geometry in ONE launch (the tiles of a manifest, the decoded
+ * tiles of a rate sweep: run_codec.py:448 -> 472 -> 475 calls compute_metrics once per tile, rate and rep).  A
+ * Case-A tile pair is 16.8 MB -- 2.6 us at HBM speed, less than a kernel launch -- so a sweep over tiles is launch
+ * bound pair by pair; here grid.y walks the pairs.  geom gives dtype / DM_BSQ / bands / rows / width / band_stride
+ * (its ref / tst are ignored); items_dev is a DEVICE array of n_items {ref, tst, sums, maxs}; every item's sums /
+ * maxs are accumulated exactly as by dm_fused_stats(plane = NULL, hist_bins = 0).  All cubes must be 16-byte
+ * aligned (the caller's contract: the array lives on the device); DM_BSQ only. */
+typedef struct dm_batch_item {
+  const void* ref;
+  const void* tst;
+  int64_t* sums;   /* DM_NSTAT x bands, accumulated */
+  int64_t* maxs;
+} dm_batch_item_t;
+int dm_fused_stats_batch(const dm_pair_t* geom, const dm_batch_item_t* items_dev, int32_t n_items, uint32_t flags,
+                         void* stream);
+
 /* per-pixel spectral pass --------------------------------------------------------------------
  * One pass over the spectral axis of every pixel.  Replaces the arithmetic of
  *   write_error_max8   quicklooks.py:123-150  (max_b |A-B|, invalid -> 0, float32 scaling -> uint8)

@@ -272,3 +272,34 @@ def test_both_gaussian_ssim_kernels_vs_oracle(variant):
         assert math.isnan(dm.ssim_gaussian_arrays(tiny, tiny, 255.0)["ssimw_b1"])
     finally:
         lib().dm_ssim_variant(0)
+
+
+@pytest.mark.parametrize("dtype", ["uint16", "int16", "uint8"])
+def test_batched_stats_equal_pair_by_pair(dtype):
+    """dm_fused_stats_batch (one launch, grid.y = pair) == dm_fused_stats per pair, bit for bit, and == the oracle."""
+    import torch
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200._lib import DM_U8, DM_U16, DM_I16
+    from image_compression_analysis_b200.engine import DevicePair, Partials, PreparedStatsBatch, Want, evaluate
+    from oracle import distortion_oracle as orc
+    rng = np.random.default_rng(7)
+    B, H, W, n = 4, 120, 136, 9                  # 16 320 pixels per band: band starts stay 16-byte aligned
+    info = np.iinfo(dtype)
+    host = []
+    for i in range(n):
+        a = rng.integers(info.min, info.max + 1, size=(B, H, W)).astype(np.int64)
+        b = np.clip(a + rng.integers(-(i + 1) * 40, (i + 1) * 40 + 1, size=a.shape), info.min, info.max)
+        host.append((a.astype(dtype), b.astype(dtype)))
+    host[3] = (host[3][0], host[3][0].copy())        # a lossless pair in the middle
+    pairs = [DevicePair.from_arrays(a, b, "bsq") for a, b in host]
+    run, outs = Partials.allocate_run(n, B, 0, pairs[0].ref.device, dtype)
+    PreparedStatsBatch(pairs, outs).launch()
+    torch.cuda.synchronize()
+    code = {"uint8": DM_U8, "uint16": DM_U16, "int16": DM_I16}[dtype]
+    for (a, b), pair, P in zip(host, pairs, outs):
+        single = evaluate(pair, Want(stats=True)).to_host()
+        h = P.to_host()
+        assert np.array_equal(h.isum, single.isum) and np.array_equal(h.imax, single.imax)
+        _check(finish.finish_compute_metrics(code, h.sums, h.maxs), orc.compute_metrics(a, b, extras=False))
+    with pytest.raises(ValueError):
+        PreparedStatsBatch(pairs[:2], outs[:1])

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
 
@@ -79,6 +80,27 @@ void report(int sms, double khz, uint32_t* out) {
   printf("%-40s %12.1f Gops/s(lane) %8.2f lane-ops/clk/SM\n", kNames[OP], best / 1e9, best / (sms * khz * 1e3));
 }
 
+// accuracy of the reciprocal / rsqrt seeds (what one or two Newton steps start from)
+__global__ void k_seed_err(double* out) {
+  double worst_rcp = 0.0, worst_rsq = 0.0;
+  unsigned long long st = 0x9E3779B97F4A7C15ull * (threadIdx.x + 1 + blockIdx.x * blockDim.x);
+  for (int i = 0; i < 4096; ++i) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    const double m = 1.0 + (double)(st >> 11) * (1.0 / 9007199254740992.0);       // [1, 2)
+    const double x = ldexp(m, (int)((st >> 3) % 200) - 100);
+    double r, q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(x));
+    worst_rcp = fmax(worst_rcp, fabs(r * x - 1.0));
+    worst_rsq = fmax(worst_rsq, fabs(q * q * x - 1.0) * 0.5);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    worst_rcp = fmax(worst_rcp, __shfl_xor_sync(0xffffffffu, worst_rcp, o));
+    worst_rsq = fmax(worst_rsq, __shfl_xor_sync(0xffffffffu, worst_rsq, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax((unsigned long long*)out, __double_as_longlong(worst_rcp)); atomicMax((unsigned long long*)out + 1, __double_as_longlong(worst_rsq)); }
+}
+
 int main() {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
@@ -89,5 +111,10 @@ int main() {
   report<I2D_S64>(sms, khz, out); report<RCP64H>(sms, khz, out); report<RSQ64H>(sms, khz, out); report<LDS32>(sms, khz, out);
   report<DFMA_IMADW>(sms, khz, out); report<DFMA_I2D_S64>(sms, khz, out); report<DFMA_LDS32>(sms, khz, out);
   report<DFMA_I2D_S32>(sms, khz, out); report<DFMA_IMADW_LDS>(sms, khz, out);
+  double* err; CK(cudaMalloc(&err, 16)); CK(cudaMemset(err, 0, 16));
+  k_seed_err<<<64, 256>>>(err);
+  double h[2]; CK(cudaMemcpy(h, err, 16, cudaMemcpyDeviceToHost));
+  printf("max relative error of the seeds over 6.7e7 random inputs: rcp.approx.ftz.f64 %.3e (2^%.1f)   rsqrt.approx.ftz.f64 %.3e (2^%.1f)\n",
+         h[0], log2(h[0]), h[1], log2(h[1]));
   return 0;
 }
