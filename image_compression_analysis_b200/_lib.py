@@ -74,6 +74,7 @@ SYMBOLS = {
     "dm_sobel_lmse": (C.c_int, [C.POINTER(DmPair), C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "dm_ssim_nblocks": (C.c_int, []),
     "dm_ssim_variant": (C.c_int, [C.c_int32]),
+    "dm_spectral_lanes_per_pixel": (C.c_int, [C.c_int32]),
     "dm_ssim_gauss": (C.c_int, [C.POINTER(DmPair), C.c_double, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "dm_combine_partials": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "dm_bip_to_bsq": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P]),

@@ -17,6 +17,7 @@ void count_launch();                                // one more kernel launched 
 bool launch_chaining();                             // dm_launch_chaining() state of this thread
 int fused_bip_variant();                            // dm_fused_bip_variant() state of this thread
 int ssim_variant();                                 // dm_ssim_variant() state of this thread
+int spectral_lanes_per_pixel();                     // dm_spectral_lanes_per_pixel() state of this thread
 
 #define DM_CUDA(expr)                                              \
   do {                                                             \

@@ -19,6 +19,8 @@ static thread_local int g_bip_variant = 0;
 int fused_bip_variant() { return g_bip_variant; }
 static thread_local int g_ssim_variant = 0;
 int ssim_variant() { return g_ssim_variant; }
+static thread_local int g_spec_lpp = 0;
+int spectral_lanes_per_pixel() { return g_spec_lpp; }
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -111,6 +113,12 @@ int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
   if (!p) return fail(DM_EARG, "dm_fused_bsq: null pair");
   return launch_fused_bsq(*p, plane, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g, lut_z, cap_z, err8_z,
                           hist8_z, static_cast<cudaStream_t>(stream));
+}
+
+int dm_spectral_lanes_per_pixel(int32_t v) {
+  if (v != 0 && v != 8 && v != 16 && v != 32) return fail(DM_EARG, "dm_spectral_lanes_per_pixel: 0 (auto), 8, 16 or 32");
+  dm::g_spec_lpp = v;
+  return DM_OK;
 }
 
 int dm_ssim_variant(int32_t v) {

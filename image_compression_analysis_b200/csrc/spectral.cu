@@ -263,51 +263,89 @@ spectral_warp_bip(SpecArgs g) {
 }
 
 
-// BIP, 16-bit samples, SAM / SID only (no error planes): one warp per pixel with the spectrum held in
-// REGISTERS as 32-bit words (two bands per lane and load, 128 contiguous bytes per warp load), so the
-// second sweep SID needs (after the minimum and the sum are known) re-reads nothing.  The SID term is
-// evaluated branch-free in the common case:  with d = ap - rp and s = ap + rp + 2e-15,
-//   ap*ln(a/r) + rp*ln(r/a) = d * ln(a/r) = d * 2 atanh(d / s)
-// (a = ap + 1e-15, r = rp + 1e-15: a - r = d and a + r = s up to one rounding), the quotient through a
-// float32 reciprocal seed and two Newton steps instead of a double division (whose slow-path branch
-// fences the library routine).  |d/s| >= 0.05 (large relative errors, typically dark bands at high
-// compression) takes log() in a second, warp-uniformly guarded step.
-template <int DT, int NWL>
-__global__ void __launch_bounds__(kSpecThreads)
+// BIP, 16-bit samples, SAM / SID only (no error planes): a GROUP of LPP lanes per pixel (32 / LPP pixels per warp)
+// with the spectrum held in REGISTERS as 32-bit words (two bands per lane and load), so the second sweep SID needs
+// (after the minimum and the sum are known) re-reads nothing.  With one warp per pixel the per-PIXEL work -- four
+// reductions, the set-up of the SID constants, the float64 finish of SAM in one lane -- was most of the kernel for
+// EnMAP's 180 bands (5.6 samples per lane); with 8 lanes per pixel the same instructions serve four pixels.
+//
+// SID from ONE exact numerator per sample.  With a' = a - amin, r' = r - rmin (integers >= 0), eps = 1e-12,
+// SA = sum a' + B eps, SR = sum r' + B eps (the integer parts exact), the reference's (run_codec.py:334-339)
+//   Ap - Rp = n / (SA SR),   n = (a' + eps) SR - (r' + eps) SA
+//   (Ap + 1e-15) / (Rp + 1e-15) = (1 + z) / (1 - z),   z = n / D,   D = (a'+eps) SR + (r'+eps) SA + 2e-15 SA SR
+// so the term (Ap - Rp) ln(..) = n * 2 atanh(z) / (SA SR): two fused multiply-adds give n and D straight from the
+// integer samples (a' SR and r' SA are exact products < 2^53 up to the eps parts, so the cancellation in n costs
+// nothing -- this is where the float64 quotients Ap, Rp of the reference lose their digits, not here), 1/D is a
+// MUFU.RCP64H seed + one Newton step (2^-40), atanh is six odd terms (|z| < 0.12: next term < 7e-13).  Every term is
+// >= 0, so a relative error of 1e-12 per term is 1e-12 on the sum.  14 FP64 operations and no conversion-unit instruction
+// per sample; 1 / (SA SR) is applied once per pixel.  |z| >= 0.12 (the bands where a spectrum has its minimum, dark
+// bands with a large relative error) takes the reference's own expression with log(): those samples -- typically
+// one or two per pixel, scattered over lanes and register slots -- are COMPACTED through a group-private list and
+// evaluated side by side, one per lane, behind a warp-uniform guard.
+template <int LPP>
+__device__ __forceinline__ int group_add(int v) {
+  if (LPP == 32) return __reduce_add_sync(0xffffffffu, v);
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPP>
+__device__ __forceinline__ int group_min(int v) {
+  if (LPP == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPP>
+__device__ __forceinline__ long long group_add_ll(long long v) {
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double splice_u32(int v) {      // exact int -> float64 for 0 <= v < 2^31 (one subtraction)
+  return __hiloint2double(0x43300000, v) - 4503599627370496.0;
+}
+
+template <int DT, int NWL, int LPP>
+__global__ void __launch_bounds__(kSpecThreads, 2)
 spectral_warp_bip16(SpecArgs g) {
-  __shared__ double red[3][kSpecThreads / 32];
-  __shared__ int2 slow_list[kSpecThreads / 32][2 * NWL * 32];       // SID: (a', r') of the samples that need log()
+  constexpr int PPW = 32 / LPP;                                      // pixels per warp
+  constexpr int WARPS = kSpecThreads / 32;
+  __shared__ double red[3][WARPS];
+  __shared__ uint32_t slow_list[WARPS][PPW][2 * NWL * LPP];         // SID: a' | r' << 16 (both < 2^16) of the samples that need log()
   const uint32_t* ref = static_cast<const uint32_t*>(g.ref);
   const uint32_t* tst = static_cast<const uint32_t*>(g.tst);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane / LPP, sl = lane % LPP;                       // pixel of the warp, lane of the pixel's group
   const int B = (int)g.bands, WPX = B >> 1;
-  double s_acos = 0.0, s_n = 0.0;                  // meaningful in lane 0
+  double s_acos = 0.0, s_n = 0.0;                  // meaningful in the first lane of every group
   double s_sid = 0.0;                              // per LANE: SID is a plain sum over pixels and bands, so the
                                                    // lanes' shares meet once, at the end of the kernel
-  const int64_t wstride = (int64_t)gridDim.x * (kSpecThreads / 32);
+  const int64_t wstride = (int64_t)gridDim.x * WARPS * PPW;
   uint32_t x[NWL], y[NWL], nx[NWL], ny[NWL];
   auto fetch = [&](int64_t p, uint32_t (&a)[NWL], uint32_t (&b)[NWL]) {
     const int64_t base = p * (int64_t)WPX;
 #pragma unroll
     for (int j = 0; j < NWL; ++j) {
-      const int idx = lane + 32 * j;
-      if (idx < WPX) { a[j] = __ldg(ref + base + idx); b[j] = __ldg(tst + base + idx); }
+      const int idx = sl + LPP * j;
+      if (idx < WPX && p < g.npix) { a[j] = __ldg(ref + base + idx); b[j] = __ldg(tst + base + idx); }
       else { a[j] = 0; b[j] = 0; }
     }
   };
-  int64_t p = (int64_t)blockIdx.x * (kSpecThreads / 32) + warp;
-  if (p < g.npix) fetch(p, nx, ny);
-  for (; p < g.npix; p += wstride) {
+  int64_t p0 = ((int64_t)blockIdx.x * WARPS + warp) * PPW;          // first pixel of this warp's current visit
+  fetch(p0 + sub, nx, ny);
+  for (; p0 < g.npix; p0 += wstride) {
+    const int64_t p = p0 + sub;
 #pragma unroll
     for (int j = 0; j < NWL; ++j) { x[j] = nx[j]; y[j] = ny[j]; }
-    if (p + wstride < g.npix) fetch(p + wstride, nx, ny);        // the next pixel's spectrum, in flight during this one
-    const uint8_t v = g.plane ? g.plane[p] : (uint8_t)0xff;
-    if (!(v & DM_VALID_SPECTRAL)) continue;
+    fetch(p + wstride, nx, ny);                                      // the next pixel's spectrum, in flight during this one
+    // a group whose pixel is past the end or masked out runs along on zeros and contributes nothing
+    const bool ok = p < g.npix && ((g.plane ? g.plane[p] : (uint8_t)0xff) & DM_VALID_SPECTRAL);
     int sa = 0, sr = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
     long long dot = 0, na2 = 0, nr2 = 0;
 #pragma unroll
     for (int j = 0; j < NWL; ++j) {
-      if (lane + 32 * j < WPX) {
+      if (sl + LPP * j < WPX) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int a = sample16<DT>(x[j], h), r = sample16<DT>(y[j], h);
@@ -316,13 +354,12 @@ spectral_warp_bip16(SpecArgs g) {
         }
       }
     }
-    // one REDUX per quantity instead of five shuffle steps
-    sa = __reduce_add_sync(0xffffffffu, sa); sr = __reduce_add_sync(0xffffffffu, sr);
-    amin = __reduce_min_sync(0xffffffffu, amin); rmin = __reduce_min_sync(0xffffffffu, rmin);
-    if (lane == 0) s_n += 1.0;
+    sa = group_add<LPP>(sa); sr = group_add<LPP>(sr);
+    amin = group_min<LPP>(amin); rmin = group_min<LPP>(rmin);
+    if (sl == 0 && ok) s_n += 1.0;
     if (g.want_sam) {
-      dot = warp_sum_ll(dot); na2 = warp_sum_ll(na2); nr2 = warp_sum_ll(nr2);
-      if (lane == 0) {
+      dot = group_add_ll<LPP>(dot); na2 = group_add_ll<LPP>(na2); nr2 = group_add_ll<LPP>(nr2);
+      if (sl == 0 && ok) {
         const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
         const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
         double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
@@ -331,59 +368,51 @@ spectral_warp_bip16(SpecArgs g) {
       }
     }
     if (g.want_sid) {
-      // SID from ONE exact numerator per sample.  With a' = a - amin, r' = r - rmin (integers >= 0), eps = 1e-12,
-      // SA = sum a' + B eps, SR = sum r' + B eps (the integer parts exact), the reference's (run_codec.py:334-339)
-      //   Ap - Rp = n / (SA SR),   n = (a' + eps) SR - (r' + eps) SA
-      //   (Ap + 1e-15) / (Rp + 1e-15) = (1 + z) / (1 - z),   z = n / D,   D = (a'+eps) SR + (r'+eps) SA + 2e-15 SA SR
-      // so the term (Ap - Rp) ln(..) = n * 2 atanh(z) / (SA SR): two fused multiply-adds give n and D straight from the
-      // integer samples (a' SR and r' SA are exact products < 2^53 up to the eps parts, so the cancellation in n
-      // costs nothing -- this is where the float64 quotients Ap, Rp of the reference lose their digits, not here),
-      // 1/D is a MUFU.RCP64H seed + two Newton steps, atanh is six odd terms (|z| < 0.12: next term < 7e-13).  Every
-      // term is >= 0, so a relative error of 1e-12 per term is 1e-12 on the sum.  15 FP64 operations and no
-      // conversion-unit instruction per sample (was ~30 + 3); 1 / (SA SR) is applied once per pixel.  |z| >= 0.12
-      // (the bands where a spectrum has its minimum, large relative errors) takes the reference's own expression
-      // with log() behind a warp-uniform guard.
-      const double SAi = (double)((long long)sa - (long long)B * amin), SRi = (double)((long long)sr - (long long)B * rmin);
-      const double SA = SAi + (double)B * 1e-12, SR = SRi + (double)B * 1e-12;
+      // sum a' <= 256 * 65535 * 2 < 2^31: the integer parts go through the mantissa splice like the samples
+      const double SA = splice_u32(sa - B * amin) + (double)B * 1e-12, SR = splice_u32(sr - B * rmin) + (double)B * 1e-12;
       const double cE = -1e-12 * (SR - SA);                            // P2 = r' SA + cE
       const double cD = 2.0 * SR * fma(1e-15, SA, 1e-12);              // D = a' SR + P2 + cD
       double t = 0.0;
       unsigned slow_mask = 0;                                          // bit 2j+h: this lane's sample needs log()
 #pragma unroll
       for (int j = 0; j < NWL; ++j) {
-        const bool have = lane + 32 * j < WPX;
+        const bool have = ok && sl + LPP * j < WPX;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           // int -> float64 by splicing the non-negative integer into the mantissa of 2^52 (one exact subtraction;
           // the conversion instruction costs two FP64-pipe slots, tools/ubench_fp64.cu)
-          const double ad = __hiloint2double(0x43300000, sample16<DT>(x[j], h) - amin) - 4503599627370496.0;
-          const double rd = __hiloint2double(0x43300000, sample16<DT>(y[j], h) - rmin) - 4503599627370496.0;
+          const double ad = splice_u32(sample16<DT>(x[j], h) - amin), rd = splice_u32(sample16<DT>(y[j], h) - rmin);
           const double p2 = fma(rd, SA, cE);
           const double n = fma(ad, SR, -p2);
           const double D = fma(ad, SR, p2) + cD;
           double q;
           asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(D));
-          q = fma(fma(-D, q, kAtanhC[5]), q, q);
-          q = fma(fma(-D, q, kAtanhC[5]), q, q);
-          const double z = n * q, z2 = z * z;
+          q = fma(fma(-D, q, kAtanhC[5]), q, q);                       // seed 2^-20 (measured) -> 2^-40: plenty for a 1e-6 gate
+          const double z = n * q, z2 = z * z, z4 = z2 * z2;
           const bool slow = __double2hiint(z2) >= 0x3f8d7dbf;         // z^2 >= 0.0144 (high word of 0.0144), i.e. |z| >= 0.12
-          double pz = kAtanhC[0];                                      // 1/11: six odd terms, next one < 0.12^12 / 13 = 7e-13
-          pz = fma(pz, z2, kAtanhC[1]);
-          pz = fma(pz, z2, kAtanhC[2]);
-          pz = fma(pz, z2, kAtanhC[3]);
-          pz = fma(pz, z2, kAtanhC[4]);
-          pz = fma(pz, z2, kAtanhC[5]);
-          t = fma(n, (have && !slow) ? z * pz : 0.0, t);
+          // six odd terms of atanh(z) / z in z^2, Estrin form (three short chains instead of five dependent steps);
+          // the next term is < 0.12^12 / 13 = 7e-13
+          const double e0 = fma(z2, kAtanhC[4], kAtanhC[5]);           // 1 + z2/3
+          const double e1 = fma(z2, kAtanhC[2], kAtanhC[3]);           // 1/5 + z2/7
+          const double e2 = fma(z2, kAtanhC[0], kAtanhC[1]);           // 1/9 + z2/11
+          const double pz = fma(z4, fma(z4, e2, e1), e0);
+          if (have && !slow) t = fma(n, z * pz, t);
           slow_mask |= (have && slow) ? (1u << (2 * j + h)) : 0u;
         }
       }
-      t *= 2.0 / (SA * SR);
+      // 2 / (SA SR): seed + two Newton steps (SA SR >= (B eps)^2 ~ 3e-20 and <= 2^62: no exponent trouble)
+      {
+        const double ss = SA * SR;
+        double q;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(ss));
+        q = fma(fma(-ss, q, 1.0), q, q);
+        q = fma(fma(-ss, q, 1.0), q, q);
+        t *= 2.0 * q;
+      }
       if (__any_sync(0xffffffffu, slow_mask != 0)) {
-        // The samples that need log() -- typically one or two per pixel (the band of the minimum when the two spectra
-        // have it in different places, dark bands with a large relative error), scattered over lanes and register
-        // slots -- are COMPACTED through a warp-private list and evaluated side by side, one per lane: one pass
-        // through the library code per pixel instead of one per occupied register slot (up to 2 NWL).
-        int2* list = slow_list[warp];
+        uint32_t* list = slow_list[warp][sub];
+        const unsigned gmask = LPP == 32 ? 0xffffffffu : (((1u << LPP) - 1u) << (sub * LPP));
+        const unsigned below = gmask & ((1u << lane) - 1u);          // lanes of this group in front of this one
         int base = 0;
 #pragma unroll
         for (int j = 0; j < NWL; ++j) {
@@ -391,17 +420,19 @@ spectral_warp_bip16(SpecArgs g) {
           for (int h = 0; h < 2; ++h) {
             const bool mine = (slow_mask >> (2 * j + h)) & 1u;
             const unsigned b = __ballot_sync(0xffffffffu, mine);
-            if (mine) list[base + __popc(b & ((1u << lane) - 1u))] = make_int2(sample16<DT>(x[j], h) - amin, sample16<DT>(y[j], h) - rmin);
-            base += __popc(b);
+            if (mine) list[base + __popc(b & below)] = (uint32_t)(sample16<DT>(x[j], h) - amin) | ((uint32_t)(sample16<DT>(y[j], h) - rmin) << 16);
+            base += __popc(b & gmask);
           }
         }
         __syncwarp();
-        const double iSA = 1.0 / SA, iSR = 1.0 / SR;
-        const double eA = 1e-12 * iSA, eR = 1e-12 * iSR;
-        for (int i = lane; i < base; i += 32) {
-          const int2 v = list[i];
-          const double ap = fma((double)v.x, iSA, eA), rp = fma((double)v.y, iSR, eR);      // run_codec.py:334-337
-          t += (ap - rp) * log((ap + 1e-15) / (rp + 1e-15));                                   // :338-339
+        if (base > 0) {
+          const double iSA = 1.0 / SA, iSR = 1.0 / SR;
+          const double eA = 1e-12 * iSA, eR = 1e-12 * iSR;
+          for (int i = sl; i < base; i += LPP) {
+            const uint32_t v = list[i];
+            const double ap = fma((double)(v & 0xffffu), iSA, eA), rp = fma((double)(v >> 16), iSR, eR);   // run_codec.py:334-337
+            t += (ap - rp) * log((ap + 1e-15) / (rp + 1e-15));                                   // :338-339
+          }
         }
         __syncwarp();
       }
@@ -409,11 +440,12 @@ spectral_warp_bip16(SpecArgs g) {
     }
   }
   s_sid = warp_sum_f64(s_sid);
+  s_acos = warp_sum_f64(s_acos); s_n = warp_sum_f64(s_n);           // (zero outside the groups' first lanes)
   if (lane == 0) { red[0][warp] = s_acos; red[1][warp] = s_sid; red[2][warp] = s_n; }
   __syncthreads();
   if (tid < 32 && g.acc) {
     double t0 = 0, t1 = 0, t2 = 0;
-    for (int w = 0; w < kSpecThreads / 32; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    for (int w = 0; w < WARPS; ++w) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
     ordered_block_sum3(t0, t1, t2, g.ws, g.acc);
   }
 }
@@ -453,12 +485,22 @@ int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_o
   // SAM / SID only on a 16-bit BIP cube: the register-resident warp kernel
   if (bip && !errmax_out && !err8_g && !err8_z && (want_sam || want_sid) && p.dtype != DM_U8 && p.bands % 2 == 0 &&
       p.bands <= 512 && ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 3) == 0) {
-    const int nwl = (int)((p.bands / 2 + 31) / 32);
-#define DM_SPEC16(DT)                                                                       \
-    do {                                                                                    \
-      if (nwl <= 3) spectral_warp_bip16<DT, 3><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);     \
-      else if (nwl <= 4) spectral_warp_bip16<DT, 4><<<kSpecBlocks, kSpecThreads, 0, s>>>(g); \
-      else spectral_warp_bip16<DT, 8><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);              \
+    // lanes per pixel: 8 while a pixel's words fit 12 per lane (<= 192 bands: EnMAP's 180 -> four pixels per warp),
+    // then 16, then the whole warp
+    const int wpx = (int)(p.bands / 2);
+    int lpp = spectral_lanes_per_pixel();                                // dm_spectral_lanes_per_pixel(): 0 = auto
+    // measured on the Case-B cube (r02e): SID 627 / 510 / 509 us and SAM + SID 760 / 674 / 832 us with 8 / 16 / 32 lanes
+    // per pixel (8 lanes need 12 words per lane for 180 bands and spill at 128 registers)
+    if (lpp == 0) lpp = wpx <= 8 * 6 ? 8 : (wpx <= 16 * 8 ? 16 : 32);
+    if ((lpp == 8 && wpx > 8 * 12) || (lpp == 16 && wpx > 16 * 8)) lpp = 32;
+#define DM_SPEC16(DT)                                                                                   \
+    do {                                                                                                \
+      if (lpp == 8 && wpx <= 8 * 6) spectral_warp_bip16<DT, 6, 8><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);          \
+      else if (lpp == 8) spectral_warp_bip16<DT, 12, 8><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);        \
+      else if (lpp == 16 && wpx <= 16 * 6) spectral_warp_bip16<DT, 6, 16><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);  \
+      else if (lpp == 16) spectral_warp_bip16<DT, 8, 16><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);       \
+      else if (wpx <= 32 * 3) spectral_warp_bip16<DT, 3, 32><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);   \
+      else spectral_warp_bip16<DT, 8, 32><<<kSpecBlocks, kSpecThreads, 0, s>>>(g);                      \
     } while (0)
     if (p.dtype == DM_I16) DM_SPEC16(DM_I16); else DM_SPEC16(DM_U16);
 #undef DM_SPEC16

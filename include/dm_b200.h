@@ -157,6 +157,12 @@ int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
                 const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
                 int32_t want_sam, int32_t want_sid, double* spectral_acc, void* workspace, void* stream);
 
+/* lanes that share one pixel in the register-resident SAM / SID kernel of dm_spectral (16-bit BIP cubes, no planes):
+ * 0 = by band count (8 lanes up to 96 bands, 16 up to 256 -- two pixels per warp for EnMAP's 180 --, else 32),
+ * 8 / 16 / 32 = pin (a choice the band count does not fit falls back to 32).  Thread-local; for A/B measurements
+ * and the parity tests, which cover every grouping. */
+int dm_spectral_lanes_per_pixel(int32_t lanes);
+
 /* one-pass BIP kernel: dm_fused_stats (moments, no histogram) + dm_spectral (error planes, SAM) from a
  * SINGLE read of both cubes -- the tile is staged once in shared memory by TMA bulk copies and
  * consumed by a per-band and a per-pixel warp group.  Same outputs and conventions as the two

@@ -303,3 +303,30 @@ def test_batched_stats_equal_pair_by_pair(dtype):
         _check(finish.finish_compute_metrics(code, h.sums, h.maxs), orc.compute_metrics(a, b, extras=False))
     with pytest.raises(ValueError):
         PreparedStatsBatch(pairs[:2], outs[:1])
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_sid_sam_every_lane_grouping_vs_oracle(lanes):
+    """dm_spectral_lanes_per_pixel: the register-resident SAM / SID kernel with 8, 16 or 32 lanes per pixel (four,
+    two, one pixel per warp), at band counts that fill the last register word partially, with int16 + nodata,
+    a caller mask (groups of a warp differ in validity) and an image whose pixel count is not a multiple of four."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200 import synth
+    from image_compression_analysis_b200._lib import check, lib
+    from oracle import distortion_oracle as orc
+    check(lib().dm_spectral_lanes_per_pixel(lanes))
+    try:
+        for bands, dtype in ((180, "uint16"), (180, "int16"), (46, "uint16"), (242, "int16"), (256, "uint16")):
+            ref, dec = synth.case_b_pair(seed=bands, bands=bands, height=37, width=53, amp=4, dtype=dtype, layout="bsq")
+            rng = np.random.default_rng(bands)
+            dec[:, rng.integers(0, 37, 40), rng.integers(0, 53, 40)] += 700          # large relative errors: the log() list
+            ref[:, 3, 5] = 0                                                             # a zero spectrum
+            valid = synth.random_valid_mask(bands, 37, 53, 0.3)
+            kw = dict(ref_nodata=-32768, tst_nodata=-32768) if dtype == "int16" else {}
+            for v in (None, valid):
+                want = orc.compute_sam_sid_lmse_caseB(ref, dec, v, **kw)
+                got = dm.compute_sam_sid_lmse_caseB_arrays(_bip(ref), _bip(dec), v, layout="bip", **kw)
+                for k in ("sam_deg", "sid", "lmse"):
+                    assert _close(got[k], want[k]), (lanes, bands, dtype, v is not None, k, got[k], want[k])
+    finally:
+        lib().dm_spectral_lanes_per_pixel(0)

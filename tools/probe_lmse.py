@@ -18,6 +18,15 @@ def t(fn, n=8):
     for _ in range(n): fn()
     e1.record(); e1.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
+from image_compression_analysis_b200._lib import lib
+for lpp in (8, 16, 32):
+    lib().dm_spectral_lanes_per_pixel(lpp)
+    for wn, want in (("sid", Want(stats=False, sid=True)), ("sam+sid", Want(stats=False, sam=True, sid=True))):
+        P = Partials.allocate(B, 0, ref.device, "uint16")
+        us = t(lambda: evaluate(bip, want, out=P))
+        P.zero_(); evaluate(bip, want, out=P); torch.cuda.synchronize()
+        print(f"bip {wn:8s} lanes/pixel {lpp:2d} {us:9.1f} us  {4*B*H*W/us/1e3:8.1f} GB/s   spec {P.spec.cpu().numpy().tolist()}", flush=True)
+lib().dm_spectral_lanes_per_pixel(0)
 for name, pair in (("bip", bip), ("bsq", bsq)):
     for wn, want in (("lmse", Want(stats=False, lmse=True)), ("sid", Want(stats=False, sid=True)), ("sam+sid", Want(stats=False, sam=True, sid=True))):
         P = Partials.allocate(B, 0, ref.device, "uint16")

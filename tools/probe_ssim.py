@@ -6,7 +6,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
 def mk(B, H, W, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    ref = torch.randint(0, 2048, (B, H, W), device="cuda", dtype=torch.int16, generator=g) * 16
+    ref = torch.randint(0, 2040, (B, H, W), device="cuda", dtype=torch.int16, generator=g) * 16
     tst = (ref + 16 * torch.randint(-3, 4, (B, H, W), device="cuda", dtype=torch.int16, generator=g)).clamp_(0, 32767)
     return DevicePair(ref, tst, "uint16", "bsq", B, H, W)
 def t(fn, n=6):
