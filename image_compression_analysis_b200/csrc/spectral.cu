@@ -306,10 +306,17 @@ __device__ __forceinline__ double splice_u32(int v) {      // exact int -> float
   return __hiloint2double(0x43300000, v) - 4503599627370496.0;
 }
 
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t dp2a_lo_su(uint32_t a, uint32_t b, uint32_t c) { int r; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"((int)c)); return (uint32_t)r; }
+__device__ __forceinline__ uint32_t dp2a_hi_ss(uint32_t a, uint32_t b, uint32_t c) { int r; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"((int)c)); return (uint32_t)r; }
+__device__ __forceinline__ uint32_t vmin_u16x2(uint32_t a, uint32_t b) { uint32_t r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
 template <int DT, int NWL, int LPP>
 __global__ void __launch_bounds__(kSpecThreads, 2)
 spectral_warp_bip16(SpecArgs g) {
   constexpr int PPW = 32 / LPP;                                      // pixels per warp
+  constexpr uint32_t OFS = DT == DM_I16 ? 0x80008000u : 0u;          // int16 -> offset binary, both halves of a word
   constexpr int WARPS = kSpecThreads / 32;
   __shared__ double red[3][WARPS];
   __shared__ uint32_t slow_list[WARPS][PPW][2 * NWL * LPP];         // SID: a' | r' << 16 (both < 2^16) of the samples that need log()
@@ -341,47 +348,74 @@ spectral_warp_bip16(SpecArgs g) {
     fetch(p + wstride, nx, ny);                                      // the next pixel's spectrum, in flight during this one
     // a group whose pixel is past the end or masked out runs along on zeros and contributes nothing
     const bool ok = p < g.npix && ((g.plane ? g.plane[p] : (uint8_t)0xff) & DM_VALID_SPECTRAL);
-    int sa = 0, sr = 0, amin = 0x7fffffff, rmin = 0x7fffffff;
-    long long dot = 0, na2 = 0, nr2 = 0;
+    // First sweep, SIMD-in-word on the packed pairs of samples (int16 in offset binary, u = x ^ 0x8000: order and
+    // differences are those of the signed values): sums by dp2a against 0x0101, minima by VIMNMX.U16x2; SAM's three
+    // products as dp2a lo/hi byte partials (x * lo8(y) and x * hi8(y), PRMT splits the bytes) -- 2 + 4 instructions
+    // per sample where scalar code spent ~8 and three quarter-rate 64-bit multiply-adds.
+    uint32_t su_a = 0, su_r = 0, mn_a = 0xffffffffu, mn_r = 0xffffffffu;
+    uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0;
 #pragma unroll
     for (int j = 0; j < NWL; ++j) {
       if (sl + LPP * j < WPX) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int a = sample16<DT>(x[j], h), r = sample16<DT>(y[j], h);
-          sa += a; sr += r; amin = min(amin, a); rmin = min(rmin, r);
-          if (g.want_sam) { dot += (long long)a * r; na2 += (long long)a * a; nr2 += (long long)r * r; }
+        const uint32_t ux = x[j] ^ OFS, uy = y[j] ^ OFS;
+        su_a = dp2a_lo_uu(ux, 0x0101u, su_a); su_r = dp2a_lo_uu(uy, 0x0101u, su_r);
+        mn_a = vmin_u16x2(mn_a, ux); mn_r = vmin_u16x2(mn_r, uy);
+        if (g.want_sam) {
+          const uint32_t px = __byte_perm(x[j], 0, 0x3120), py = __byte_perm(y[j], 0, 0x3120);
+          if (DT == DM_I16) {      // signed samples: s16 x (unsigned low byte) and s16 x (signed high byte)
+            xxl = dp2a_lo_su(x[j], px, xxl); xxh = dp2a_hi_ss(x[j], px, xxh);
+            yyl = dp2a_lo_su(y[j], py, yyl); yyh = dp2a_hi_ss(y[j], py, yyh);
+            xyl = dp2a_lo_su(x[j], py, xyl); xyh = dp2a_hi_ss(x[j], py, xyh);
+          } else {
+            xxl = dp2a_lo_uu(x[j], px, xxl); xxh = dp2a_hi_uu(x[j], px, xxh);
+            yyl = dp2a_lo_uu(y[j], py, yyl); yyh = dp2a_hi_uu(y[j], py, yyh);
+            xyl = dp2a_lo_uu(x[j], py, xyl); xyh = dp2a_hi_uu(x[j], py, xyh);
+          }
         }
       }
     }
-    sa = group_add<LPP>(sa); sr = group_add<LPP>(sr);
-    amin = group_min<LPP>(amin); rmin = group_min<LPP>(rmin);
+    const int sa = group_add<LPP>((int)su_a), sr = group_add<LPP>((int)su_r);                 // sums of u (< 2^31)
+    const int amin = group_min<LPP>((int)min(mn_a & 0xffffu, mn_a >> 16));
+    const int rmin = group_min<LPP>((int)min(mn_r & 0xffffu, mn_r >> 16));
     if (sl == 0 && ok) s_n += 1.0;
     if (g.want_sam) {
-      dot = group_add_ll<LPP>(dot); na2 = group_add_ll<LPP>(na2); nr2 = group_add_ll<LPP>(nr2);
+      // lo + 256 * hi: each part fits 32 bits up to 256 bands x 2 lanes' shares, the sum is an exact float64
+      const int t_xxl = group_add<LPP>((int)xxl), t_xxh = group_add<LPP>((int)xxh), t_yyl = group_add<LPP>((int)yyl);
+      const int t_yyh = group_add<LPP>((int)yyh), t_xyl = group_add<LPP>((int)xyl), t_xyh = group_add<LPP>((int)xyh);
       if (sl == 0 && ok) {
-        const double na = __dadd_rn(__dsqrt_rn((double)na2), 1e-12);
-        const double nr = __dadd_rn(__dsqrt_rn((double)nr2), 1e-12);
-        double c = __ddiv_rn((double)dot, __dmul_rn(na, nr));
+        double na2, nr2, dot;
+        if (DT == DM_I16) {
+          na2 = fma((double)t_xxh, 256.0, (double)t_xxl); nr2 = fma((double)t_yyh, 256.0, (double)t_yyl);
+          dot = fma((double)t_xyh, 256.0, (double)t_xyl);
+        } else {
+          na2 = fma((double)(uint32_t)t_xxh, 256.0, (double)(uint32_t)t_xxl); nr2 = fma((double)(uint32_t)t_yyh, 256.0, (double)(uint32_t)t_yyl);
+          dot = fma((double)(uint32_t)t_xyh, 256.0, (double)(uint32_t)t_xyl);
+        }
+        const double na = __dadd_rn(__dsqrt_rn(na2), 1e-12);
+        const double nr = __dadd_rn(__dsqrt_rn(nr2), 1e-12);
+        double c = __ddiv_rn(dot, __dmul_rn(na, nr));
         c = fmin(1.0, fmax(-1.0, c));
         s_acos += acos(c);
       }
     }
     if (g.want_sid) {
-      // sum a' <= 256 * 65535 * 2 < 2^31: the integer parts go through the mantissa splice like the samples
+      // sum a' <= 512 * 65535 < 2^31: the integer parts go through the mantissa splice like the samples
       const double SA = splice_u32(sa - B * amin) + (double)B * 1e-12, SR = splice_u32(sr - B * rmin) + (double)B * 1e-12;
       const double cE = -1e-12 * (SR - SA);                            // P2 = r' SA + cE
       const double cD = 2.0 * SR * fma(1e-15, SA, 1e-12);              // D = a' SR + P2 + cD
+      const uint32_t amin2 = (uint32_t)amin * 0x10001u, rmin2 = (uint32_t)rmin * 0x10001u;
       double t = 0.0;
       unsigned slow_mask = 0;                                          // bit 2j+h: this lane's sample needs log()
 #pragma unroll
       for (int j = 0; j < NWL; ++j) {
         const bool have = ok && sl + LPP * j < WPX;
+        // a' and r' of both samples of the word with one subtraction each (no borrow: every half >= its minimum)
+        const uint32_t dx = (x[j] ^ OFS) - amin2, dy = (y[j] ^ OFS) - rmin2;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           // int -> float64 by splicing the non-negative integer into the mantissa of 2^52 (one exact subtraction;
           // the conversion instruction costs two FP64-pipe slots, tools/ubench_fp64.cu)
-          const double ad = splice_u32(sample16<DT>(x[j], h) - amin), rd = splice_u32(sample16<DT>(y[j], h) - rmin);
+          const double ad = splice_u32((int)(h ? dx >> 16 : dx & 0xffffu)), rd = splice_u32((int)(h ? dy >> 16 : dy & 0xffffu));
           const double p2 = fma(rd, SA, cE);
           const double n = fma(ad, SR, -p2);
           const double D = fma(ad, SR, p2) + cD;
@@ -420,7 +454,10 @@ spectral_warp_bip16(SpecArgs g) {
           for (int h = 0; h < 2; ++h) {
             const bool mine = (slow_mask >> (2 * j + h)) & 1u;
             const unsigned b = __ballot_sync(0xffffffffu, mine);
-            if (mine) list[base + __popc(b & below)] = (uint32_t)(sample16<DT>(x[j], h) - amin) | ((uint32_t)(sample16<DT>(y[j], h) - rmin) << 16);
+            if (mine) {
+              const uint32_t dx = (x[j] ^ OFS) - amin2, dy = (y[j] ^ OFS) - rmin2;
+              list[base + __popc(b & below)] = h ? (dx >> 16) | (dy & 0xffff0000u) : (dx & 0xffffu) | (dy << 16);
+            }
             base += __popc(b & gmask);
           }
         }
@@ -484,7 +521,7 @@ int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_o
   g.acc = (want_sam || want_sid) ? spectral_acc : nullptr; g.ws = workspace;
   // SAM / SID only on a 16-bit BIP cube: the register-resident warp kernel
   if (bip && !errmax_out && !err8_g && !err8_z && (want_sam || want_sid) && p.dtype != DM_U8 && p.bands % 2 == 0 &&
-      p.bands <= 512 && ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 3) == 0) {
+      p.bands <= 256 /* 32-bit dp2a partials of a pixel */ && ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 3) == 0) {
     // lanes per pixel: 8 while a pixel's words fit 12 per lane (<= 192 bands: EnMAP's 180 -> four pixels per warp),
     // then 16, then the whole warp
     const int wpx = (int)(p.bands / 2);
