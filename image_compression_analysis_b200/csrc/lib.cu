@@ -122,7 +122,7 @@ int dm_spectral_lanes_per_pixel(int32_t v) {
 }
 
 int dm_ssim_variant(int32_t v) {
-  if (v != 0 && v != 1) return fail(DM_EARG, "dm_ssim_variant: 0 (tiled kernel) or 1 (streaming kernel)");
+  if (v < 0 || v > 3) return fail(DM_EARG, "dm_ssim_variant: 0 (auto), 1 (integer streaming kernel), 2 (tiled kernel), 3 (ring kernel)");
   dm::g_ssim_variant = v;
   return DM_OK;
 }

@@ -356,6 +356,199 @@ ssim_stream_kernel(const StreamArgs g) {
   ordered_band_sum<2>(t, g.scratch, static_cast<Workspace*>(g.workspace)->band_counter, accs, &red[0][0]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ring kernel (the default for 16-bit cubes with an even width).  What the captures of the tiled kernel say
+// (profiles/r02l_ncu_ssim_tiled.txt): 282 instructions per band pixel of which 136 on the FP64 pipe, pipe 58 % busy,
+// issue slots 60 % -- neither saturated; the time goes to three block barriers per tile at two CTAs per SM, to
+// dependency waits, and to work done twice (18 % halo rows in the horizontal pass, conversions and products per
+// 4-output group).  Same arithmetic (all float64, 11-tap separable), different schedule:
+//
+//   * a 128-thread block owns a strip of 128 output columns and STREAMS down a row segment in steps of 11 input
+//     rows: no row is filtered twice (a segment pays 10 warm-up rows once), three independent blocks per SM
+//   * stage: cp.async copies of 32-bit words (two pixels) one step ahead, straight into a double-buffered 12.7 KB
+//     block of shared memory (no registers held across the passes)
+//   * pass H: one item = (row, 4 neighbouring columns): seven words of each cube by three LDS.64 + one LDS.32, float64
+//     through the 2^52 mantissa splice (int16 in offset binary), products once per input and item, 176 DFMA,
+//     results to a 45 KB plane block
+//     in a lane-major order (column 4 g + o lives at o * 32 + g) so that writes and reads are conflict free
+//   * pass V: thread = column, the 11 rows of the step in order, each a SCATTER into 11 pending outputs held in
+//     registers (44 accumulators; with 11 rows per step every phase is static): each horizontal result is read once
+//     (4 LDS.64) and used 11 times -- against 9.7 shared loads per output and plane, and 4 % recomputation, before
+//   * SSIM from {E x, E y, E(x^2+y^2), E xy}; the quotient as MUFU.RCP64H + two Newton steps
+// 157 instructions per band pixel (122 FP64), two barriers per 11 rows.  Measured (r02q): 5.87 ms per 10980^2 x 4 scene
+// against 6.16 ms -- 5 %, not the 35 % the instruction count promised: ncu (profiles/r02n_ncu_ssim_ring_first.txt) shows
+// the FP64 pipe 49 % busy at three warps per scheduler against 58 % at four in the tiled kernel; a pure DFMA stream needs
+// neither (tools/ubench_dfma_occ.cu: 12 warps per SM with 16 chains reach 95 %), so what is left are the fixed-latency
+// waits between the shared-memory loads and the DFMA blocks that consume them, uneven rows per warp (11 rows on 4 warps)
+// and the barriers.  Small images (segments shorter than ~120 rows) stay on the tiled kernel.
+constexpr int kRingThreads = 128;
+constexpr int RS = 128;                 // output columns per strip
+constexpr int RR = 2 * RAD + 1;         // input rows per step
+constexpr int RWORDS = (RS + 2 * RAD) / 2;                 // 69 32-bit words (two pixels) per row and cube
+constexpr int RPITCH = 72;              // words per staged row and cube (69 used; 288 bytes: rows stay 16-byte aligned)
+constexpr int RPRE = (RR * RWORDS + kRingThreads - 1) / kRingThreads;   // 6 words per thread, cube and step
+constexpr int kRingSmem = 2 * 2 * RR * RPITCH * 4 + RR * 4 * RS * 8;
+
+struct RingArgs {
+  const void* ref;
+  const void* tst;
+  int64_t band_stride, width, buf_rows;
+  int64_t r_lo, r_hi;                 // counted buffer rows
+  int seg_rows, strips_x;
+  int64_t nseg;
+  double w[2 * RAD + 1];
+  double c1, c2;
+  double* scratch; double* sum_acc; double* cnt_acc; void* workspace;
+};
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(kRingThreads, 3)
+ssim_ring_kernel(const RingArgs g) {
+  extern __shared__ __align__(16) unsigned char ring_smem[];
+  uint32_t (*raw)[2][RR][RPITCH] = reinterpret_cast<uint32_t (*)[2][RR][RPITCH]>(ring_smem);              // [2 buffers][x | y]
+  double (*hres)[4][RS] = reinterpret_cast<double (*)[4][RS]>(ring_smem + 2 * 2 * RR * RPITCH * 4);         // [RR]
+  __shared__ double red[2][32];
+  constexpr uint32_t OFS2 = SIGNED ? 0x80008000u : 0u;
+  constexpr double kSplice = 4503599627370496.0;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int band = blockIdx.y;
+  const uint32_t* A = reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(g.ref) + (int64_t)band * g.band_stride);
+  const uint32_t* R = reinterpret_cast<const uint32_t*>(static_cast<const uint16_t*>(g.tst) + (int64_t)band * g.band_stride);
+  const int64_t c_lo = RAD, c_hi = g.width - RAD;
+  const int64_t wrow = g.width >> 1;                       // words per image row
+  double acc_s = 0.0;
+  unsigned acc_n = 0;
+  double va[RR][4];                    // pending vertical sums: slot a started at the row with phase a
+  const uint32_t raw_base = (uint32_t)__cvta_generic_to_shared(ring_smem);
+  const int64_t ntasks = g.nseg * g.strips_x;
+  for (int64_t task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const int64_t seg = task / g.strips_x;
+    const int strip = (int)(task - seg * g.strips_x);
+    const int64_t r0 = g.r_lo + seg * g.seg_rows;
+    const int64_t r1 = r0 + g.seg_rows < g.r_hi ? r0 + g.seg_rows : g.r_hi;
+    const int64_t c0 = c_lo + (int64_t)strip * RS;
+    const int64_t col = c0 + 4 * lane + warp;              // pass V: the column whose plane values sit at position t
+    const bool col_ok = col < c_hi;
+    const int n_in = (int)(r1 - r0) + 2 * RAD;             // input rows r0-5 .. r1+4
+    const int nsteps = (n_in + RR - 1) / RR;
+    const int64_t w0 = (c0 - RAD) >> 1;                    // first word of the strip in a row (c0 - 5 is even)
+    const int64_t wmax = wrow - 1;
+    // stage the words of step `st` (rows st*11 .. +10) straight into shared memory with cp.async: no registers are
+    // held across the filter passes (a register prefetch spilled, and a spilled load is a synchronous load).
+    // Rows / words past the data are clamped: they only feed outputs that are never counted.
+    auto stage = [&](int st) {
+      if (st < nsteps) {
+#pragma unroll
+        for (int k = 0; k < RPRE; ++k) {
+          const int e = t + kRingThreads * k;
+          if (e < RR * RWORDS) {
+            const int rr = e / RWORDS, wc = e - rr * RWORDS;
+            int64_t ri = r0 - RAD + (int64_t)st * RR + rr;
+            ri = ri >= g.buf_rows ? g.buf_rows - 1 : ri;
+            int64_t wi = w0 + wc;
+            wi = wi > wmax ? wmax : wi;
+            const uint32_t dst = raw_base + (uint32_t)((((st & 1) * 2 + 0) * RR + rr) * RPITCH + wc) * 4u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(A + ri * wrow + wi) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(RR * RPITCH * 4)), "l"(R + ri * wrow + wi) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    __syncthreads();                   // the previous task's last pass H has read its rows
+    stage(0);
+    for (int st = 0; st < nsteps; ++st) {
+      stage(st + 1);                   // buffer (st+1)&1 was last read by pass H of step st-1, before that step's barrier
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this thread's copies of step st have landed
+      __syncthreads();                 // ... everybody's have; and pass V of the previous step has read the plane block
+      // ---- pass H: items (row, group of 4 columns); row = warp + 4 k, group = lane
+      {
+        const uint32_t (*bx)[RPITCH] = raw[st & 1][0];
+        const uint32_t (*by)[RPITCH] = raw[st & 1][1];
+#pragma unroll 1
+        for (int row = warp; row < RR; row += kRingThreads / 32) {
+          // 14 pixels from pixel 4 * lane: seven words of each cube from word 2 * lane (8-byte aligned)
+          uint32_t xw[7], yw[7];
+          {
+            const uint2* qx = reinterpret_cast<const uint2*>(&bx[row][2 * lane]);
+            const uint2* qy = reinterpret_cast<const uint2*>(&by[row][2 * lane]);
+            const uint2 a = qx[0], b = qx[1], c = qx[2];
+            const uint2 d = qy[0], e = qy[1], f = qy[2];
+            xw[0] = a.x; xw[1] = a.y; xw[2] = b.x; xw[3] = b.y; xw[4] = c.x; xw[5] = c.y; xw[6] = bx[row][2 * lane + 6];
+            yw[0] = d.x; yw[1] = d.y; yw[2] = e.x; yw[3] = e.y; yw[4] = f.x; yw[5] = f.y; yw[6] = by[row][2 * lane + 6];
+          }
+          double x[14], y[14];
+#pragma unroll
+          for (int k = 0; k < 14; ++k) {
+            const uint32_t wx = xw[k >> 1] ^ OFS2, wy = yw[k >> 1] ^ OFS2;
+            x[k] = __hiloint2double(0x43300000, (int)((k & 1) ? wx >> 16 : wx & 0xffffu)) - kSplice;
+            y[k] = __hiloint2double(0x43300000, (int)((k & 1) ? wy >> 16 : wy & 0xffffu)) - kSplice;
+          }
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl) {
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < 14; ++k) {
+              const double v = pl == 0 ? x[k] : pl == 1 ? y[k] : pl == 2 ? fma(x[k], x[k], y[k] * y[k]) : x[k] * y[k];
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+                if (k - o >= 0 && k - o <= 2 * RAD) a4[o] = fma(g.w[k - o], v, a4[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) hres[row][pl][o * 32 + lane] = a4[o];
+          }
+        }
+      }
+      __syncthreads();
+      // ---- pass V: thread = column; the rows of the step in order, static phases
+#pragma unroll
+      for (int rr = 0; rr < RR; ++rr) {
+        const int sidx = st * RR + rr;
+        if (sidx < n_in) {
+          double h[4];
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl) h[pl] = hres[rr][pl][t];
+#pragma unroll
+          for (int a = 0; a < RR; ++a) {
+            const int tap = (rr - a + RR) % RR;
+            const double wt = g.w[tap];
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl) va[a][pl] = tap == 0 ? wt * h[pl] : fma(wt, h[pl], va[a][pl]);
+          }
+          if (sidx >= 2 * RAD && col_ok) {
+            constexpr int dummy = 0; (void)dummy;
+            const int a = (rr + 1) % RR;
+            const double ux1 = va[a][0], uy1 = va[a][1], uq = va[a][2], up = va[a][3];
+            const double ux = SIGNED ? ux1 - 32768.0 : ux1, uy = SIGNED ? uy1 - 32768.0 : uy1;
+            const double vsum = uq - fma(ux1, ux1, uy1 * uy1);          // var x + var y (shift invariant)
+            const double vxy = fma(-ux1, uy1, up);                     // covariance (shift invariant)
+            const double num = fma(2.0, ux * uy, g.c1) * fma(2.0, vxy, g.c2);
+            const double den = fma(ux, ux, fma(uy, uy, g.c1)) * (vsum + g.c2);
+            double q;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(den));
+            q = fma(fma(-den, q, 1.0), q, q);
+            q = fma(fma(-den, q, 1.0), q, q);
+            acc_s = fma(num, q, acc_s);
+            acc_n += 1u;
+          }
+        }
+      }
+    }
+  }
+  acc_s = warp_sum_f64(acc_s);
+  double cnt = warp_sum_f64((double)acc_n);
+  __syncthreads();
+  if (lane == 0) { red[0][warp] = acc_s; red[1][warp] = cnt; }
+  __syncthreads();
+  double tt[2] = {0.0, 0.0};
+  if (t == 0) {
+    for (int w = 0; w < kRingThreads / 32; ++w) { tt[0] += red[0][w]; tt[1] += red[1][w]; }
+  }
+  __syncthreads();
+  double* const accs[2] = {g.sum_acc, g.cnt_acc};
+  ordered_band_sum<2>(tt, g.scratch, static_cast<Workspace*>(g.workspace)->band_counter, accs, &red[0][0]);
+}
+
 }  // namespace
 
 int ssim_nblocks() { return kSsimBlocks; }
@@ -380,7 +573,45 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
   for (int k = -RAD; k <= RAD; ++k) { taps.w[k + RAD] = std::exp(-0.5 / (1.5 * 1.5) * (double)(k * k)); sum += taps.w[k + RAD]; }
   for (int k = 0; k <= 2 * RAD; ++k) taps.w[k] /= sum;
   const double c1 = (0.01 * L) * (0.01 * L), c2 = (0.03 * L) * (0.03 * L);
-  if (ssim_variant() == 1) {
+  const int variant = ssim_variant();
+  const bool ring_ok = p.dtype != DM_U8 && (p.width & 1) == 0 && (p.band_stride & 1) == 0 && p.width >= 2 * RAD + 2 &&
+                       ((reinterpret_cast<uintptr_t>(p.ref) | reinterpret_cast<uintptr_t>(p.tst)) & 3) == 0;
+  // blocks per band of the ring kernel: a fixed function of the band count (the summation order must not depend on
+  // the device); 444 = 3 resident blocks on each of 148 SMs
+  int nbx = (int)(444 / p.bands);
+  nbx = nbx < 2 ? 2 : (nbx > kSsimBlocks ? kSsimBlocks : nbx);
+  // the ring kernel pays 10 warm-up rows per segment: it is the choice when the image is large enough that segments
+  // of >= 122 rows still give every block two tasks (measured r02q: 10980^2 x 4 scene 5.87 ms against 6.16 ms tiled;
+  // a 1024^2 x 4 tile 93 us against 70 us)
+  const int64_t ring_cols = p.width - 2 * RAD, ring_rows = (r_hi > r_lo ? r_hi - r_lo : 0);
+  const bool ring_big = ((ring_cols + RS - 1) / RS) * ((ring_rows + 121) / 122) >= 2 * (int64_t)nbx;
+  if (((variant == 0 && ring_big) || variant == 3) && ring_ok) {
+    RingArgs g;
+    g.ref = p.ref; g.tst = p.tst; g.band_stride = p.band_stride; g.width = p.width; g.buf_rows = p.rows;
+    g.r_lo = r_lo; g.r_hi = r_hi > r_lo ? r_hi : r_lo;
+    for (int k = 0; k <= 2 * RAD; ++k) g.w[k] = taps.w[k];
+    g.c1 = c1; g.c2 = c2;
+    g.scratch = scratch; g.sum_acc = sum_acc; g.cnt_acc = cnt_acc; g.workspace = workspace;
+    const int64_t ncols = p.width - 2 * RAD, nrows = g.r_hi - g.r_lo;
+    g.strips_x = ncols > 0 ? (int)((ncols + RS - 1) / RS) : 0;
+    // segments of 11 m - 10 rows (11 m input rows: whole steps); long ones pay their 10 warm-up rows once, short
+    // ones give every block of a small image something to do
+    int m = 24;
+    while (m > 3 && (int64_t)g.strips_x * ((nrows + (RR * m - 2 * RAD) - 1) / (RR * m - 2 * RAD)) < 3 * (int64_t)nbx) m -= 3;
+    g.seg_rows = RR * m - 2 * RAD;
+    g.nseg = nrows > 0 ? (nrows + g.seg_rows - 1) / g.seg_rows : 0;
+    const dim3 rgrid((unsigned)nbx, (unsigned)p.bands);
+    if (p.dtype == DM_I16) {
+      DM_CUDA(cudaFuncSetAttribute(ssim_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
+      ssim_ring_kernel<true><<<rgrid, kRingThreads, kRingSmem, s>>>(g);
+    } else {
+      DM_CUDA(cudaFuncSetAttribute(ssim_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmem));
+      ssim_ring_kernel<false><<<rgrid, kRingThreads, kRingSmem, s>>>(g);
+    }
+    DM_LAUNCH_CHECK("ssim_ring");
+    return DM_OK;
+  }
+  if (variant == 1) {
     StreamArgs g;
     g.ref = p.ref; g.tst = p.tst; g.band_stride = p.band_stride; g.width = p.width; g.buf_rows = p.rows;
     g.r_lo = r_lo; g.r_hi = r_hi > r_lo ? r_hi : r_lo;

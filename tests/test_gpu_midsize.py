@@ -237,10 +237,11 @@ def test_strip_path_all_false_mask_means_unmasked():
     _check(finish.finish_compute_metrics(1, tot.sums, tot.maxs), orc.compute_metrics(ref, dec, lower, extras=False))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_both_gaussian_ssim_kernels_vs_oracle(variant):
-    """dm_ssim_variant: 0 = tiled all-FP64 kernel (default), 1 = streaming kernel (integer horizontal pass in a 31-bit
-    fixed-point window, register-resident vertical scatter).  Both against the scipy oracle at a size where every warp of the
+    """dm_ssim_variant: 0 = auto (ring kernel for 16-bit cubes of even width, else tiled), 1 = warp-streaming kernel
+    (integer horizontal pass in a 31-bit fixed-point window), 2 = tiled all-FP64 kernel, 3 = ring kernel (row-streaming,
+    all FP64, register-resident vertical scatter).  Both against the scipy oracle at a size where every warp of the
     streaming kernel runs several tasks and both trip copies of its unrolled row loop (segments > 22 rows), with odd
     sizes (partial last strip / segment), int16 (offset-binary path) and uint8."""
     import image_compression_analysis_b200 as dm
@@ -251,7 +252,9 @@ def test_both_gaussian_ssim_kernels_vs_oracle(variant):
         rng = np.random.default_rng(90 + variant)
         for dtype, L, amp, shape in (("uint16", 65535.0, 2500, (2, 701, 333)), ("int16", 8191.0, 120, (1, 300, 130)),
                                      ("uint8", 255.0, 6, (3, 97, 75)), ("uint16", 4095.0, 40, (1, 11, 11)),
-                                     ("uint16", 4095.0, 40, (1, 12, 43))):
+                                     ("uint16", 4095.0, 40, (1, 12, 43)), ("uint16", 65535.0, 900, (2, 533, 398)),
+                                     ("int16", 32767.0, 3000, (1, 97, 268)), ("uint16", 4095.0, 40, (1, 12, 12)),
+                                     ("uint16", 4095.0, 40, (3, 11, 140))):
             info = np.iinfo(dtype)
             a = rng.integers(info.min, info.max + 1, size=shape).astype(np.int64)
             b = np.clip(a + rng.integers(-amp, amp + 1, size=shape), info.min, info.max)
