@@ -76,7 +76,10 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
     // front of them.  Element e = threadIdx.x + 256 k of the tile is row e / 42, column e % 42; clamped
     // indices are only reached by outputs that are discarded.
     constexpr int NPRE = (IH * IW + 255) / 256;          // 11
-    uint32_t pre[NPRE];
+    // the two samples of an element stay in SEPARATE registers until they are staged: packing them right behind the
+    // loads (one register per element) made the pack instruction wait for the loads -- the "prefetch" was a
+    // synchronous load in front of pass H (ncu r02l: 20 % of the stall samples on those four IMADs)
+    uint32_t pre_a[NPRE], pre_b[NPRE];
     auto fetch_tile = [&](int64_t t) {
       const int64_t r0 = r_lo + (t / tiles_x) * SH, c0 = c_lo + (t % tiles_x) * SW;
 #pragma unroll
@@ -86,9 +89,8 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
         int64_t r = r0 + lr - RAD, c = c0 + lc - RAD;
         r = r < 0 ? 0 : (r >= buf_rows ? buf_rows - 1 : r);
         c = c < 0 ? 0 : (c >= width ? width - 1 : c);
-        const uint32_t a = e < IH * IW ? (uint32_t)(uint16_t)A[r * width + c] : 0u;
-        const uint32_t b = e < IH * IW ? (uint32_t)(uint16_t)R[r * width + c] : 0u;
-        pre[k] = a | (b << 16);
+        pre_a[k] = e < IH * IW ? (uint32_t)(uint16_t)A[r * width + c] : 0u;
+        pre_b[k] = e < IH * IW ? (uint32_t)(uint16_t)R[r * width + c] : 0u;
       }
     };
     if ((int64_t)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
@@ -103,8 +105,8 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
           const int lr = e / IW, lc = e - lr * IW;
           // samples go to shared memory in offset binary (int16: x ^ 0x8000), i.e. as non-negative integers
           // below 2^16, which pass H turns into float64 with the 2^52 splice (see there)
-          xs[lr][lc] = (int)((pre[k] & 0xffffu) ^ OFS);
-          ys[lr][lc] = (int)((pre[k] >> 16) ^ OFS);
+          xs[lr][lc] = (int)(pre_a[k] ^ OFS);
+          ys[lr][lc] = (int)(pre_b[k] ^ OFS);
         }
       }
       __syncthreads();
@@ -357,7 +359,7 @@ ssim_stream_kernel(const StreamArgs g) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Ring kernel (the default for 16-bit cubes with an even width).  What the captures of the tiled kernel say
+// Ring kernel (dm_ssim_variant(3); 16-bit cubes with an even width).  What the captures of the tiled kernel say
 // (profiles/r02l_ncu_ssim_tiled.txt): 282 instructions per band pixel of which 136 on the FP64 pipe, pipe 58 % busy,
 // issue slots 60 % -- neither saturated; the time goes to three block barriers per tile at two CTAs per SM, to
 // dependency waits, and to work done twice (18 % halo rows in the horizontal pass, conversions and products per
@@ -380,7 +382,8 @@ ssim_stream_kernel(const StreamArgs g) {
 // the FP64 pipe 49 % busy at three warps per scheduler against 58 % at four in the tiled kernel; a pure DFMA stream needs
 // neither (tools/ubench_dfma_occ.cu: 12 warps per SM with 16 chains reach 95 %), so what is left are the fixed-latency
 // waits between the shared-memory loads and the DFMA blocks that consume them, uneven rows per warp (11 rows on 4 warps)
-// and the barriers.  Small images (segments shorter than ~120 rows) stay on the tiled kernel.
+// and the barriers.  With the tiled kernel's prefetch repaired (it packed the loaded samples right behind the loads,
+// i.e. waited for them: 20 % of its stall samples) the tiled kernel is the faster one again: 5.71 ms.
 constexpr int kRingThreads = 128;
 constexpr int RS = 128;                 // output columns per strip
 constexpr int RR = 2 * RAD + 1;         // input rows per step
@@ -580,12 +583,10 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
   // the device); 444 = 3 resident blocks on each of 148 SMs
   int nbx = (int)(444 / p.bands);
   nbx = nbx < 2 ? 2 : (nbx > kSsimBlocks ? kSsimBlocks : nbx);
-  // the ring kernel pays 10 warm-up rows per segment: it is the choice when the image is large enough that segments
-  // of >= 122 rows still give every block two tasks (measured r02q: 10980^2 x 4 scene 5.87 ms against 6.16 ms tiled;
-  // a 1024^2 x 4 tile 93 us against 70 us)
-  const int64_t ring_cols = p.width - 2 * RAD, ring_rows = (r_hi > r_lo ? r_hi - r_lo : 0);
-  const bool ring_big = ((ring_cols + RS - 1) / RS) * ((ring_rows + 121) / 122) >= 2 * (int64_t)nbx;
-  if (((variant == 0 && ring_big) || variant == 3) && ring_ok) {
+  // variant 0 (auto) is the tiled kernel: with its prefetch fixed (r02r) it does the 10980^2 x 4 scene in 5.71 ms against
+  // 5.86 ms for the ring kernel, and a 1024^2 x 4 tile in 70 us against 93 us (the ring kernel pays 10 warm-up rows per
+  // segment, which small images cannot amortise).  The ring kernel runs on request (dm_ssim_variant(3)).
+  if (variant == 3 && ring_ok) {
     RingArgs g;
     g.ref = p.ref; g.tst = p.tst; g.band_stride = p.band_stride; g.width = p.width; g.buf_rows = p.rows;
     g.r_lo = r_lo; g.r_hi = r_hi > r_lo ? r_hi : r_lo;

@@ -226,13 +226,12 @@ int dm_sobel_lmse(const dm_pair_t* p, int64_t row_begin, int64_t row_end, int64_
  * The buffer must hold 5 halo rows on each side that is not an image border.  1..2048 bands. */
 int dm_ssim_nblocks(void);
 /* which Gaussian-SSIM kernel dm_ssim_gauss launches (thread-local):
- *   0  the measured choice: the row-streaming "ring" kernel for LARGE 16-bit images with an even width (segments of
- *      >= 122 rows for every block), the tiled kernel else
- *   3  the ring kernel where it applies (all float64; 128-column strips streamed 11 rows at a time, vertical pass
- *      as a register scatter), else tiled      2  the shared-memory tiled all-FP64 kernel (any geometry)
- *   1  the warp-streaming kernel with an exact integer horizontal pass (measured slowest on B200: IMAD.WIDE runs
- *      at a third of the DFMA rate)
- * All three are checked against both oracles by the parity tests. */
+ *   0 / 2  the shared-memory tiled all-FP64 kernel (any geometry; the measured choice: 5.71 ms per 10980^2 x 4 scene)
+ *   3  the row-streaming "ring" kernel where it applies (16-bit cubes of even width; all float64, 128-column strips
+ *      streamed 11 rows at a time, cp.async staging, vertical pass as a register scatter: 5.86 ms), else tiled
+ *   1  the warp-streaming kernel with an exact integer horizontal pass (8.98 ms: IMAD.WIDE runs at a third of the
+ *      DFMA rate on B200)
+ * Three independent implementations of one definition; the parity tests check each against both oracles. */
 int dm_ssim_variant(int32_t variant);
 int dm_ssim_gauss(const dm_pair_t* p, double data_range, int64_t row_begin, int64_t row_end,
                   int64_t img_row0, int64_t img_rows, double* scratch, double* sum_acc, double* cnt_acc,
