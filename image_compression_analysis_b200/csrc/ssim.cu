@@ -646,6 +646,8 @@ int launch_ssim_gauss(const dm_pair_t& p, double L, int64_t row_begin, int64_t r
     DM_LAUNCH_CHECK("ssim_stream");
     return DM_OK;
   }
+  // 296 blocks per band (four "waves" for a 4-band image): the hardware hands out blocks as slots free up, so many short
+  // blocks balance better than one resident wave of long ones (74 per band, tried r02t: scene 6.01 ms against 5.71 ms)
   const dim3 grid(kSsimBlocks, (unsigned)p.bands);
 #define DM_SSIM(T)                                                                                           \
   do {                                                                                                       \

@@ -217,10 +217,21 @@ def error_max8_pair(pair: DevicePair, err_max_global=255, err_max_zoom=None, pct
     if len(caps) > 1:
         lz = to_device(caps[1][0])
         oz = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
-    check(lib().dm_spectral(C.byref(cp), engine._ptr(plane), None,
-                            engine._ptr(lg), lg.numel() - 1, engine._ptr(og), engine._ptr(P.hist8_g),
-                            engine._ptr(lz), 0 if lz is None else lz.numel() - 1, engine._ptr(oz), engine._ptr(P.hist8_z),
-                            0, 0, None, None, st))
+    from . import _lib
+    plane_args = (engine._ptr(lg), lg.numel() - 1, engine._ptr(og), engine._ptr(P.hist8_g),
+                  engine._ptr(lz), 0 if lz is None else lz.numel() - 1, engine._ptr(oz), engine._ptr(P.hist8_z))
+    # the one-pass kernels write the planes at HBM speed where they apply (16-bit BIP cubes with a multiple of four
+    # bands -- EnMAP through ingest's transposition --, BSQ cubes of up to four bands -- Case A); their per-band
+    # statistics land in P and are not used here.  Everything else takes the per-pixel spectral pass.
+    rc = _lib.DM_EUNSUPPORTED
+    if pair.layout == "bip":
+        rc = lib().dm_fused_bip(C.byref(cp), engine._ptr(plane), engine._ptr(P.sums), engine._ptr(P.imax), None, *plane_args,
+                                0, None, None, st)
+    elif pair.bands <= 4:
+        rc = lib().dm_fused_bsq(C.byref(cp), engine._ptr(plane), engine._ptr(P.sums), engine._ptr(P.imax), None, *plane_args, st)
+    if rc == _lib.DM_EUNSUPPORTED:
+        rc = lib().dm_spectral(C.byref(cp), engine._ptr(plane), None, *plane_args, 0, 0, None, None, st)
+    check(rc)
     h = P.to_host()
     err8_g = og.cpu().numpy().reshape(H, W)
     err8_z = None if oz is None else oz.cpu().numpy().reshape(H, W)
