@@ -39,7 +39,9 @@ constexpr int VSEG = 7;                                 // outputs per thread in
 constexpr int HP = SW + 1;                              // row pitch of the float64 planes (odd: see pass H)
 constexpr int PH = IH + 2;                              // plane rows incl. two never-written rows that only
                                                         // discarded outputs of the last segment read
-constexpr int kSsimSmem = 2 * IH * (IW + 1) * 4 + 4 * PH * HP * 8;
+constexpr int XP = IW + 2;                              // row pitch of the staged samples: 44 ints = 176 bytes, so that pass H reads its
+                                                        // 14 inputs as three LDS.128 + one LDS.64 (rows 176 B apart: conflict free)
+constexpr int kSsimSmem = 2 * IH * XP * 4 + 4 * PH * HP * 8;
 
 struct Taps { double w[2 * RAD + 1]; };
 
@@ -49,9 +51,9 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
                   int64_t r_lo, int64_t r_hi, int64_t buf_rows, Taps taps, double c1, double c2, double* scratch,
                   double* sum_acc, double* cnt_acc, void* workspace) {
   extern __shared__ __align__(16) unsigned char ssim_smem[];
-  int (*xs)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem);
-  int (*ys)[IW + 1] = reinterpret_cast<int (*)[IW + 1]>(ssim_smem + IH * (IW + 1) * 4);
-  double (*hp)[PH][HP] = reinterpret_cast<double (*)[PH][HP]>(ssim_smem + 2 * IH * (IW + 1) * 4);   // [4][PH][HP]
+  int (*xs)[XP] = reinterpret_cast<int (*)[XP]>(ssim_smem);
+  int (*ys)[XP] = reinterpret_cast<int (*)[XP]>(ssim_smem + IH * XP * 4);
+  double (*hp)[PH][HP] = reinterpret_cast<double (*)[PH][HP]>(ssim_smem + 2 * IH * XP * 4);   // [4][PH][HP]
   __shared__ double red[2][32];
   const int band = blockIdx.y;
   const T* A = ref + (int64_t)band * band_stride;
@@ -80,8 +82,31 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
     // loads (one register per element) made the pack instruction wait for the loads -- the "prefetch" was a
     // synchronous load in front of pass H (ncu r02l: 20 % of the stall samples on those four IMADs)
     uint32_t pre_a[NPRE], pre_b[NPRE];
+    // element k of this thread sits at (lr, lc) of every tile: its offset from the tile's first staged sample is fixed.
+    // Tiles whose staged window lies inside the buffer (all but the last tile row / column) need no clamping, and
+    // the clamps with their 64-bit compares were ~35 instructions per output pixel of a kernel that waits for
+    // its non-FP64 phases (r0 >= 5 and c0 >= 5 always: only the upper edges can stick out).
+    uint32_t off[NPRE];
+#pragma unroll
+    for (int k = 0; k < NPRE; ++k) {
+      const int e = threadIdx.x + 256 * k;
+      const int lr = e / IW, lc = e - lr * IW;
+      off[k] = (uint32_t)lr * (uint32_t)width + (uint32_t)lc;
+    }
+    const bool fits32 = width < (int64_t)(1 << 24);
     auto fetch_tile = [&](int64_t t) {
       const int64_t r0 = r_lo + (t / tiles_x) * SH, c0 = c_lo + (t % tiles_x) * SW;
+      if (fits32 && r0 - RAD + IH <= buf_rows && c0 - RAD + IW <= width) {
+        const T* a0 = A + (r0 - RAD) * width + (c0 - RAD);
+        const T* b0 = R + (r0 - RAD) * width + (c0 - RAD);
+#pragma unroll
+        for (int k = 0; k < NPRE; ++k) {
+          const bool have = k < NPRE - 1 || threadIdx.x + 256 * k < IH * IW;
+          pre_a[k] = have ? (uint32_t)(uint16_t)a0[off[k]] : 0u;
+          pre_b[k] = have ? (uint32_t)(uint16_t)b0[off[k]] : 0u;
+        }
+        return;
+      }
 #pragma unroll
       for (int k = 0; k < NPRE; ++k) {
         const int e = threadIdx.x + 256 * k;
@@ -112,18 +137,29 @@ ssim_gauss_kernel(const T* __restrict__ ref, const T* __restrict__ tst, int64_t 
       __syncthreads();
       if (t + gridDim.x < ntiles) fetch_tile(t + gridDim.x);
       // ---- pass H: item = (group of 4 output columns, row lr); 512 items, two per thread.  The ROW is
-      // the fastest thread index: the lanes of a warp read the same columns of 32 rows (43 words apart)
+      // the fastest thread index: the lanes of a warp read the same columns of 32 rows (44 words apart, 16-byte vectors)
       // and write the same columns of 32 plane rows (33 doubles apart) -- both strides odd, conflict free.
 #pragma unroll 1
       for (int item = threadIdx.x; item < IH * (SW / 4); item += 256) {
         const int lr = item & (IH - 1), g4 = (item >> 6) * 4;
         double vx[14], vy[14], vq[14], vp[14];
+        int xi[16], yi[16];              // the item's 14 inputs (+2) of both cubes: three LDS.128 + one LDS.64 each
+        {
+          const int4* qx = reinterpret_cast<const int4*>(&xs[lr][g4]);
+          const int4* qy = reinterpret_cast<const int4*>(&ys[lr][g4]);
+          const int4 a = qx[0], b = qx[1], c = qx[2], d = qy[0], e = qy[1], f = qy[2];
+          const int2 gx = *reinterpret_cast<const int2*>(&xs[lr][g4 + 12]), gy = *reinterpret_cast<const int2*>(&ys[lr][g4 + 12]);
+          xi[0] = a.x; xi[1] = a.y; xi[2] = a.z; xi[3] = a.w; xi[4] = b.x; xi[5] = b.y; xi[6] = b.z; xi[7] = b.w;
+          xi[8] = c.x; xi[9] = c.y; xi[10] = c.z; xi[11] = c.w; xi[12] = gx.x; xi[13] = gx.y;
+          yi[0] = d.x; yi[1] = d.y; yi[2] = d.z; yi[3] = d.w; yi[4] = e.x; yi[5] = e.y; yi[6] = e.z; yi[7] = e.w;
+          yi[8] = f.x; yi[9] = f.y; yi[10] = f.z; yi[11] = f.w; yi[12] = gy.x; yi[13] = gy.y;
+        }
 #pragma unroll
         for (int k = 0; k < 14; ++k) {
           // int -> float64 without the conversion unit (I2F.F64 costs two FP64-pipe slots here, measured): the
           // sample spliced into the mantissa of 2^52 IS 2^52 + u; one exact subtraction gives u (or u - 32768)
-          const double x = __hiloint2double(0x43300000, xs[lr][g4 + k]) - kSplice;
-          const double y = __hiloint2double(0x43300000, ys[lr][g4 + k]) - kSplice;
+          const double x = __hiloint2double(0x43300000, xi[k]) - kSplice;
+          const double y = __hiloint2double(0x43300000, yi[k]) - kSplice;
           vx[k] = x; vy[k] = y; vq[k] = fma(x, x, y * y); vp[k] = x * y;
         }
 #pragma unroll
