@@ -13,10 +13,17 @@ allreduce of the integer / float64 partials, the path's only exchange.
 One JSON line on stdout (rank 0):
   value      whole-job GB/s with the cubes resident in HBM (CUDA events, max over ranks); launches are
              prepared once (engine.PreparedFused), every step writes its own partial vector of a run
-  e2e        the same metric through the public API from pinned HOST buffers (H2D + D2H inside)
-  roofline   the dominant kernel against the measured HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline  the numpy port of the reference (oracle/) on a bounded sample, rank 0, N=1 only
-`--impl reference` times that CPU port with all host cores instead (rank 0 only).
+  e2e        the same metric through the public API from pinned HOST buffers (H2D + D2H inside);
+             e2e.shared_original: the same sweep when the decoded cubes share ONE original (uploaded once)
+  roofline   the dominant kernel against the measured HBM copy peak (MEASURED_PEAKS.json); traffic = DRAM bytes
+             of the committed ncu capture of the same kernel instance (profiles/traffic.json says which)
+  configs    the other BASELINE.json configurations in the same run: C1 Case-A tile statistics (batched launch +
+             single-pair latency), C3 Case-A tile Gaussian SSIM + ERR8 planes, C4 the 10980 x 10980 x 4 scene with
+             every Case-A metric STRONG-scaled over the ranks, C5 the 42-cube Case-B sweep with every Case-B metric
+             sharded by pair -- each with time, GB/s of algorithmic bytes and its roofline fraction
+  cpu_baseline  the reference's CPU path (the unmodified reference when its tree is mounted, else the numpy port
+             of oracle/) on a bounded sample, one core, rank 0, N=1 only
+`--impl reference` times that CPU path with all host cores instead (rank 0 only; median step).
 """
 from __future__ import annotations
 
