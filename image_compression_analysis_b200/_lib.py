@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 DM_OK, DM_EARG, DM_ECUDA, DM_EUNSUPPORTED = 0, 1, 2, 3
 DM_U8, DM_U16, DM_I16 = 0, 1, 2
@@ -68,6 +68,8 @@ SYMBOLS = {
                               C.c_int32, C.c_int32, _P, _P, _P]),
     "dm_fused_bip": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                C.c_int32, _P, _P, _P]),
+    "dm_fused_bip_scan": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
+                                    C.c_int32, _P, _P, _P]),
     "dm_fused_bsq": (C.c_int, [C.POINTER(DmPair), _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
     "dm_sobel_mag": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "dm_sobel_nblocks": (C.c_int, []),

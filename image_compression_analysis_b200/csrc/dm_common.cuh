@@ -62,6 +62,11 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
                      uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
                      const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
                      double* spectral_acc, void* workspace, cudaStream_t s);
+int launch_fused_bip_scan(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts,
+                          int64_t* sums, int64_t* maxs,
+                          uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                          const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
+                          double* spectral_acc, void* workspace, cudaStream_t s);
 int64_t launch_validity_ct(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts,
                            cudaStream_t s, int* status);
 int launch_fused_bsq(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs, uint16_t* errmax_out,

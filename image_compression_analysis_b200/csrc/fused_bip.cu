@@ -84,6 +84,12 @@ struct FusedArgs {
   uint32_t poll_ns;           // barrier polling interval (DM_POLL_NS, default kPollNs)
   double* spec_acc;           // {sum arccos, -, n}, accumulated (ordered_block_sum3)
   void* ws;
+  // in-kernel validity scan (fused_ct_kernel<..., SCAN = true>, dm_fused_bip_scan): the rule of dm_validity
+  const uint8_t* valid_in;    // caller mask, may be null (16-byte aligned: its tile bytes ride along by bulk copy)
+  uint8_t* plane_out;         // may be null: the validity plane as a by-product
+  int64_t* counts;            // 3 x int64, accumulated (may be null)
+  int ref_has, ref_nd, tst_has, tst_nd;
+  int scan;                   // host side only: launch the SCAN build
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -590,12 +596,20 @@ __device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
   return pending == 1u;
 }
 
-template <int BANDS, int DT, bool MASK, bool ERR, int MPW>
+// SCAN (implies MASK): the validity plane is not an input but computed in the kernel.  The pixel group that
+// serves a tile first sweeps it for the nodata rules of dm_validity (OR / MIN of the spectrum XORed with the
+// packed nodata values: ~5 instructions per 8 bytes, a few hundred nanoseconds per tile), writes the tile's 64
+// validity bytes where the bulk-copied plane of the MASK variant would sit and arrives on the stage's `mask`
+// barrier; the band warps wait for THAT barrier instead of the full barrier, so they trail the data by the
+// scan only, not by the pixel group's whole SAM sweep, and the 4-stage ring keeps its slack.  One read of
+// the pair instead of two (validity pre-pass + masked kernel): run_codec.py:249-263 folded into :268-285.
+template <int BANDS, int DT, bool MASK, bool ERR, int MPW, bool SCAN = false>
 __global__ void __launch_bounds__(Geo<BANDS, MPW>::THREADS, 1)
 fused_ct_kernel(FusedArgs g) {
   using G = Geo<BANDS, MPW>;
+  static_assert(!SCAN || MASK, "the in-kernel scan feeds the masked arithmetic");
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], mask_bar[kStages];
   __shared__ unsigned h8g[256], h8z[256];
   __shared__ double red[3][kPixelWarpsCT];
   __shared__ int sh_cube[8];
@@ -608,7 +622,10 @@ fused_ct_kernel(FusedArgs g) {
   constexpr bool TRACK = MASK || DT == DM_I16;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], G::CONSUMERS); }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], G::CONSUMERS);
+      mbar_init(&mask_bar[s], kPixelWarpsCT / 2);       // SCAN: the four pixel warps that scan a tile
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 256) { h8g[tid] = 0; h8z[tid] = 0; }
@@ -624,7 +641,10 @@ fused_ct_kernel(FusedArgs g) {
   const int dbg = DM_DBG(g) | ((ERR || g.want_sam) ? 0 : 4);
   const uint32_t poll_ns = DM_POLL(g);
   const uint32_t ring = smem_u32(smem);
-  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), mask0 = smem_u32(&mask_bar[0]);
+  const bool scan_vin = SCAN && g.valid_in != nullptr;
+  // global writes inside the tile loop (error planes, the validity plane): no early start of the next launch
+  const bool loop_writes = ERR || (SCAN && g.plane_out != nullptr);
 
   auto issue_tile = [&](int it) {
     if (it >= my_tiles) return;
@@ -633,11 +653,13 @@ fused_ct_kernel(FusedArgs g) {
     if (dbg & 1) { mbar_arrive(fb); return; }
     const int64_t off = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * (int64_t)G::CUBE;
     unsigned char* dst = smem + (size_t)s * G::PITCH;
-    mbar_expect_tx(fb, G::STAGE + (MASK ? G::P : 0));
+    mbar_expect_tx(fb, G::STAGE + (SCAN ? (scan_vin ? G::P : 0) : (MASK ? G::P : 0)));
     bulk_g2s(dst, static_cast<const char*>(g.ref) + off, G::CUBE, fb);
     bulk_g2s(dst + G::CUBE, static_cast<const char*>(g.tst) + off, G::CUBE, fb);
     // the tile's validity bytes ride along, so that no consumer touches global memory in its loop
-    if (MASK) bulk_g2s(dst + G::STAGE, g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P, G::P, fb);
+    // (SCAN: the caller's mask bytes instead, behind the 64 bytes the pixel group will write)
+    if (SCAN) { if (scan_vin) bulk_g2s(dst + G::STAGE + G::P, g.valid_in + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P, G::P, fb); }
+    else if (MASK) bulk_g2s(dst + G::STAGE, g.plane + ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P, G::P, fb);
   };
   // Called by lane 0 of a consumer warp when the warp has finished reading tile `it`.  There is no
   // producer warp: every consumer warp arrives on the stage's empty barrier, and the one whose arrival
@@ -662,7 +684,7 @@ fused_ct_kernel(FusedArgs g) {
   // (below, ahead of every global write), so nothing it does early can race with what is still running
   // here.  Variants that write per-pixel planes do not trigger early: two launches may be given the same
   // planes.
-  if (!ERR) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!loop_writes) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < G::BAND_WARPS) {
     // ------------------------------------------------------------------ band group
@@ -716,7 +738,10 @@ fused_ct_kernel(FusedArgs g) {
         const int it1 = it0 + EPOCH < my_tiles ? it0 + EPOCH : my_tiles;
         for (int it = it0; it < it1; ++it) {
           const int s = it & (kStages - 1);
-          mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
+          // SCAN: the mask barrier completes after the pixel warps have seen the full barrier complete and released
+          // their writes, so it orders the tile's data as well (one wait per tile instead of two: -3 us)
+          if (SCAN) mbar_wait_a(mask0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
+          else mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
           if (!(dbg & 2)) {
             const uint32_t xs = ld_off + (uint32_t)s * G::PITCH;
             const unsigned char* pl = smem + (size_t)s * G::PITCH + G::STAGE;      // MASK: the tile's validity bytes
@@ -845,7 +870,7 @@ fused_ct_kernel(FusedArgs g) {
     // are combined with one shuffle per partial; the float64 finish is batched over two visits
     // (lanes 0-15 keep the pixels of the even visit, lanes 16-31 those of the odd one) so that all
     // 32 lanes of the warp work in it.
-    if (ERR) asm volatile("griddepcontrol.wait;" ::: "memory");   // planes are written in the tile loop
+    if (loop_writes) asm volatile("griddepcontrol.wait;" ::: "memory");   // planes are written in the tile loop
     const int tg = tid - G::BAND_THREADS;             // 0..255
     const int grp = tg >> 7;                          // tile parity this group serves
     const int wq = (tg >> 5) & 3;                     // warp of the group: pixels 16wq .. 16wq+15
@@ -858,6 +883,8 @@ fused_ct_kernel(FusedArgs g) {
     uint32_t k_xxl = 0, k_xxh = 0, k_yyl = 0, k_yyh = 0, k_xyl = 0, k_xyh = 0, k_e = 0;
     int k_it = 0;
     uint32_t k_v = 0xff;
+    const uint32_t ndr = ((uint32_t)g.ref_nd & 0xffffu) * 0x10001u, ndt = ((uint32_t)g.tst_nd & 0xffffu) * 0x10001u;
+    int c0 = 0, c1 = 0, c2 = 0;                       // SCAN: pixels with each validity bit (lanes 0-15)
 
     auto finish = [&]() {
       const int64_t p = ((int64_t)blockIdx.x + (int64_t)k_it * gridDim.x) * G::P + tp;
@@ -897,15 +924,111 @@ fused_ct_kernel(FusedArgs g) {
       }
     };
 
+    // SCAN: validity of tile `it` (the rule of validity_ct_kernel below).  Waits for the tile, publishes its 64
+    // validity bytes in the stage, arrives on the stage's mask barrier and returns this lane's pixel's byte.
+    // Lean first sweep: only the per-halfword MINIMUM of the spectrum XORed with nodata (zero <=> some band equals
+    // nodata <=> the pixel leaves compute_metrics); when nodata is the type's lowest value in both files (EnMAP's
+    // int16 -32768, Sentinel-2's 0) the minimum of the raw samples does it without the XOR.  The OR over the
+    // spectrum (dataset_mask(): some band differs from nodata) can only be zero where that minimum is zero, so a
+    // second sweep computes it just for warps that met a nodata sample (warp-uniform branch).
+    const bool nd_lowest = SCAN && (!g.ref_has || (g.ref_nd & 0xffff) == (DT == DM_I16 ? 0x8000 : 0))
+                                && (!g.tst_has || (g.tst_nd & 0xffff) == (DT == DM_I16 ? 0x8000 : 0));
+    auto scan_tile = [&](int it) -> uint32_t {
+      const int s = it & (kStages - 1);
+      mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
+      const unsigned char* xs = lane_base + (size_t)s * G::PITCH;
+      uint32_t r_min, t_min;
+      if (nd_lowest) {
+        auto lo = [&](const unsigned char* base) -> uint32_t {
+          uint32_t m = DT == DM_I16 ? 0x7fff7fffu : 0xffffffffu;
+          auto unit = [&](int j) {
+            const uint2 w = *reinterpret_cast<const uint2*>(base + 8 * j);
+            m = DT == DM_I16 ? __vimin3_s16x2(m, w.x, w.y) : __vimin3_u16x2(m, w.x, w.y);
+          };
+#pragma unroll 11
+          for (int j = 0; j < H1; ++j) unit(j);
+          if (H0 > H1 && hl == 0) unit(H1);
+          return m ^ OFS;                              // offset binary: zero <=> the lowest value was met
+        };
+        r_min = g.ref_has ? lo(xs) : 0xffffffffu;
+        t_min = g.tst_has ? lo(xs + G::CUBE) : 0xffffffffu;
+      } else {
+        auto lo = [&](const unsigned char* base, uint32_t nd2) -> uint32_t {
+          uint32_t m = 0xffffffffu;
+          auto unit = [&](int j) {
+            const uint2 w = *reinterpret_cast<const uint2*>(base + 8 * j);
+            m = __vimin3_u16x2(m, w.x ^ nd2, w.y ^ nd2);
+          };
+#pragma unroll 11
+          for (int j = 0; j < H1; ++j) unit(j);
+          if (H0 > H1 && hl == 0) unit(H1);
+          return m;
+        };
+        r_min = g.ref_has ? lo(xs, ndr) : 0xffffffffu;
+        t_min = g.tst_has ? lo(xs + G::CUBE, ndt) : 0xffffffffu;
+      }
+      r_min = vminu2(r_min, __shfl_xor_sync(0xffffffffu, r_min, 16));
+      t_min = vminu2(t_min, __shfl_xor_sync(0xffffffffu, t_min, 16));
+      const bool rl = hmin2(r_min) != 0, tl = hmin2(t_min) != 0;   // no band equals nodata
+      bool ds = true, band1 = true;
+      if (__any_sync(0xffffffffu, !(rl && tl))) {
+        // "some band differs from nodata" for the cube(s) in which this warp met a nodata sample: OR of the
+        // XORed words, or -- nodata being the lowest value -- the maximum of the raw samples (one instruction
+        // per 8 bytes instead of two)
+        auto any = [&](const unsigned char* base, uint32_t nd2) -> bool {
+          uint32_t o = nd_lowest ? (DT == DM_I16 ? 0x80008000u : 0u) : 0u;
+          auto unit = [&](int j) {
+            const uint2 w = *reinterpret_cast<const uint2*>(base + 8 * j);
+            if (nd_lowest) o = DT == DM_I16 ? __vimax3_s16x2(o, w.x, w.y) : __vimax3_u16x2(o, w.x, w.y);
+            else o |= (w.x ^ nd2) | (w.y ^ nd2);
+          };
+#pragma unroll 11
+          for (int j = 0; j < H1; ++j) unit(j);
+          if (H0 > H1 && hl == 0) unit(H1);
+          if (nd_lowest) o ^= OFS;                     // nonzero <=> some sample above the lowest value
+          o |= __shfl_xor_sync(0xffffffffu, o, 16);
+          return o != 0;
+        };
+        bool r_any = true, t_any = true, r_b1 = true, t_b1 = true;
+        if (__any_sync(0xffffffffu, !rl)) { r_any = any(xs, ndr); r_b1 = ((*reinterpret_cast<const uint32_t*>(xs) ^ ndr) & 0xffffu) != 0; }
+        if (__any_sync(0xffffffffu, !tl)) { t_any = any(xs + G::CUBE, ndt); t_b1 = ((*reinterpret_cast<const uint32_t*>(xs + G::CUBE) ^ ndt) & 0xffffu) != 0; }
+        // band 1 lives in half 0: lanes 16-31 take their partner's verdict
+        const unsigned b1 = __ballot_sync(0xffffffffu, r_b1 && t_b1);
+        band1 = (b1 >> (lane & 15)) & 1u;
+        ds = r_any && t_any;
+      }
+      unsigned char* mk = smem + (size_t)s * G::PITCH + G::STAGE;
+      const bool vin = scan_vin ? mk[G::P + tp] != 0 : true;
+      uint32_t v = 0;
+      if (ds && rl && tl && vin) v |= DM_VALID_METRICS;
+      if (ds && band1) v |= DM_VALID_QUICKLOOK;
+      if (scan_vin ? vin : ds) v |= DM_VALID_SPECTRAL;
+      if (hl == 0) {
+        mk[tp] = (unsigned char)v;
+        if (g.plane_out) g.plane_out[((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * G::P + tp] = (uint8_t)v;
+        c0 += (v & DM_VALID_METRICS) ? 1 : 0;
+        c1 += (v & DM_VALID_QUICKLOOK) ? 1 : 0;
+        c2 += (v & DM_VALID_SPECTRAL) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mask_bar[s]);
+      return v;
+    };
+
+    // SCAN: a group scans its own tile when it gets to it.  Scanning the group's NEXT tile ahead of time (before the
+    // sweep, half way through it, or between sweep and float64 finish, blocking or only when the tile has landed)
+    // was measured slower every time (216-244 us against 207 us per EnMAP cube): it delays the group's own sweep,
+    // and the stage that sweep holds is what the ring is short of.
     int visit = 0;
     for (int it = grp; it < my_tiles; it += 2, ++visit) {
       const int s = it & (kStages - 1);
-      mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
-      uint32_t emax = 0, vcur = 0xff;
+      if (!SCAN) mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);   // SCAN: scan_tile(it) waited
+      uint32_t emax = 0, vcur = 0xffu;
+      if (SCAN) vcur = scan_tile(it);
       uint32_t xxl = 0, xxh = 0, yyl = 0, yyh = 0, xyl = 0, xyh = 0;
       if (!(dbg & 4)) {
         const unsigned char* xs = lane_base + (size_t)s * G::PITCH;
-        if (MASK) vcur = smem[(size_t)s * G::PITCH + G::STAGE + tp];
+        if (MASK && !SCAN) vcur = smem[(size_t)s * G::PITCH + G::STAGE + tp];
         auto unit = [&](int j) {
           const uint2 xv = *reinterpret_cast<const uint2*>(xs + 8 * j);
           const uint2 yv = *reinterpret_cast<const uint2*>(xs + G::CUBE + 8 * j);
@@ -950,6 +1073,14 @@ fused_ct_kernel(FusedArgs g) {
     if ((visit & 1) && hl == 0 && !(dbg & 4)) finish();      // pixels of an unpaired last visit
     __syncwarp();
     asm volatile("griddepcontrol.wait;" ::: "memory");      // see the band group's flush
+    if (SCAN && g.counts) {
+      const long long t0 = warp_sum_ll(c0), t1 = warp_sum_ll(c1), t2 = warp_sum_ll(c2);
+      if (lane == 0) {
+        if (t0) atomic_add_i64(g.counts + 0, t0);
+        if (t1) atomic_add_i64(g.counts + 1, t1);
+        if (t2) atomic_add_i64(g.counts + 2, t2);
+      }
+    }
     s_acos = warp_sum_f64(s_acos); s_n = warp_sum_f64(s_n);
     const int pw = warp - G::BAND_WARPS;
     if (lane == 0) { red[0][pw] = s_acos; red[2][pw] = s_n; }
@@ -1141,9 +1272,9 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
   constexpr bool pdl_allowed = true;
 #endif
   const bool pdl = pdl_allowed && launch_chaining();
-#define DM_FUSED_CT(DT, MASK, ERR)                                                                    \
+#define DM_FUSED_CT(DT, MASK, ERR, SCAN)                                                              \
   do {                                                                                                \
-    auto k = fused_ct_kernel<BANDS, DT, MASK, ERR, MPW>;                                              \
+    auto k = fused_ct_kernel<BANDS, DT, MASK, ERR, MPW, SCAN>;                                        \
     DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));      \
     cudaLaunchConfig_t cfg = {};                                                                      \
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(G::THREADS);                              \
@@ -1155,12 +1286,15 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
     DM_CUDA(cudaLaunchKernelEx(&cfg, k, g));                                                          \
   } while (0)
   const bool err = g.errmax || g.err8_g || g.err8_z;
-  if (dtype == DM_U16) {
-    if (g.plane) { if (err) DM_FUSED_CT(DM_U16, true, true); else DM_FUSED_CT(DM_U16, true, false); }
-    else { if (err) DM_FUSED_CT(DM_U16, false, true); else DM_FUSED_CT(DM_U16, false, false); }
+  if (g.scan) {
+    if (dtype == DM_U16) { if (err) DM_FUSED_CT(DM_U16, true, true, true); else DM_FUSED_CT(DM_U16, true, false, true); }
+    else { if (err) DM_FUSED_CT(DM_I16, true, true, true); else DM_FUSED_CT(DM_I16, true, false, true); }
+  } else if (dtype == DM_U16) {
+    if (g.plane) { if (err) DM_FUSED_CT(DM_U16, true, true, false); else DM_FUSED_CT(DM_U16, true, false, false); }
+    else { if (err) DM_FUSED_CT(DM_U16, false, true, false); else DM_FUSED_CT(DM_U16, false, false, false); }
   } else {
-    if (g.plane) { if (err) DM_FUSED_CT(DM_I16, true, true); else DM_FUSED_CT(DM_I16, true, false); }
-    else { if (err) DM_FUSED_CT(DM_I16, false, true); else DM_FUSED_CT(DM_I16, false, false); }
+    if (g.plane) { if (err) DM_FUSED_CT(DM_I16, true, true, false); else DM_FUSED_CT(DM_I16, true, false, false); }
+    else { if (err) DM_FUSED_CT(DM_I16, false, true, false); else DM_FUSED_CT(DM_I16, false, false, false); }
   }
 #undef DM_FUSED_CT
   DM_LAUNCH_CHECK("fused_bip_ct");
@@ -1169,10 +1303,16 @@ int run_ct(FusedArgs g, int dtype, cudaStream_t s) {
 
 }  // namespace
 
-int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
-                     uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
-                     const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
-                     double* spectral_acc, void* workspace, cudaStream_t s) {
+namespace {
+
+// Common body of dm_fused_bip (plane = input, may be null) and dm_fused_bip_scan (scan != null: the validity
+// plane is computed in the kernel from the pair's nodata values and the caller's mask).
+struct ScanSpec { const uint8_t* valid_in; uint8_t* plane_out; int64_t* counts; };
+
+int fused_bip_impl(const char* who, const dm_pair_t& p, const uint8_t* plane, const ScanSpec* scan, int64_t* sums, int64_t* maxs,
+                   uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                   const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
+                   double* spectral_acc, void* workspace, cudaStream_t s) {
   if (!p.ref || !p.tst || !sums || !maxs) return fail(DM_EARG, "dm_fused_bip: null pointer");
   if (p.layout != DM_BIP) return fail(DM_EUNSUPPORTED, "dm_fused_bip: BIP cubes only");
   if (p.dtype != DM_U16 && p.dtype != DM_I16) return fail(DM_EUNSUPPORTED, "dm_fused_bip: 16-bit samples only");
@@ -1185,6 +1325,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_fused_bip: bad global LUT");
   if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_fused_bip: bad zoom LUT");
   if (want_sam && (!spectral_acc || !workspace)) return fail(DM_EARG, "dm_fused_bip: spectral_acc / workspace is null");
+  (void)who;
   FusedArgs g;
   g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
   g.P = 0; g.ntiles = 0; g.tail_pixels = 0; g.zero = 0;
@@ -1193,6 +1334,8 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   g.lut_z = lut_z; g.cap_z = cap_z; g.err8_z = err8_z; g.hist8_z = err8_z ? hist8_z : nullptr;
   g.want_sam = want_sam; g.spec_acc = want_sam ? spectral_acc : nullptr; g.ws = workspace;
   g.debug = 0; g.poll_ns = kPollNs;
+  g.valid_in = nullptr; g.plane_out = nullptr; g.counts = nullptr; g.scan = 0;
+  g.ref_has = p.ref_has_nodata; g.ref_nd = p.ref_nodata; g.tst_has = p.tst_has_nodata; g.tst_nd = p.tst_nodata;
 #ifdef DM_DEBUG_HOOKS
   { const char* e = getenv("DM_FUSED_DEBUG"); g.debug = e ? atoi(e) : 0; }
   { const char* e = getenv("DM_POLL_NS"); g.poll_ns = e ? (uint32_t)atoi(e) : kPollNs; }
@@ -1200,6 +1343,14 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
   if (g.npix <= 0) return DM_OK;
   const int variant = fused_bip_variant();             // dm_fused_bip_variant(): 0 auto | 12 | 23 | 1 = run-time-geometry kernel
   const bool force_generic = variant == 1 || (g.debug & 8) != 0;
+  if (scan) {
+    // the in-kernel scan exists in the specialised 180-band kernel only; a partial last tile takes the two-pass
+    // route (dm_validity's generic kernel on those < 64 pixels, then the generic one-pass kernel with that plane)
+    if (B != 180 || g.npix < kTilePixels || force_generic) return fail(DM_EUNSUPPORTED, "dm_fused_bip_scan: 180-band cubes of at least 64 pixels");
+    if (reinterpret_cast<uintptr_t>(scan->valid_in) & 15) return fail(DM_EUNSUPPORTED, "dm_fused_bip_scan: valid_in must be 16-byte aligned");
+    if (!scan->plane_out && g.npix % kTilePixels) return fail(DM_EARG, "dm_fused_bip_scan: a partial last tile needs plane_out");
+    g.scan = 1; g.valid_in = scan->valid_in; g.plane_out = scan->plane_out; g.counts = scan->counts;
+  }
   // (the specialised kernel bulk-copies the tile's 64 mask bytes: the plane must be 16-byte aligned)
   if (B == 180 && g.npix >= kTilePixels && !force_generic && !(reinterpret_cast<uintptr_t>(plane) & 15)) {
     // full 64-pixel tiles through the specialised kernel, the partial last tile through the generic one
@@ -1209,7 +1360,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
     // Measured in a sweep (bench.py): plain stats + SAM 135.5 us with 23 band warps against 137.2 us; with
     // error planes or a validity plane the 12-warp build wins (163 / 176 us against 165 / 190 us).
     // dm_fused_bip_variant(12 | 23) pins the choice (A/B runs, and the tests cover both builds).
-    bool narrow = (!plane && !errmax_out && !err8_g && !err8_z) != ((g.debug & 16) != 0);
+    bool narrow = (!plane && !scan && !errmax_out && !err8_g && !err8_z) != ((g.debug & 16) != 0);
     if (variant == 12) narrow = false; else if (variant == 23) narrow = true;
     int rc = narrow ? run_ct<180, 2>(g, p.dtype, s) : run_ct<180, 4>(g, p.dtype, s);
     if (rc != DM_OK || done == g.npix) return rc;
@@ -1220,8 +1371,36 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
     if (g.err8_g) g.err8_g += done;
     if (g.err8_z) g.err8_z += done;
     g.npix -= done;
+    if (scan) {
+      dm_pair_t q = p;
+      q.ref = g.ref; q.tst = g.tst; q.rows = 1; q.width = g.npix;
+      rc = launch_validity(q, scan->valid_in ? scan->valid_in + done : nullptr, scan->plane_out + done, scan->counts, s);
+      if (rc != DM_OK) return rc;
+      g.plane = scan->plane_out + done;
+      g.scan = 0; g.valid_in = nullptr; g.plane_out = nullptr; g.counts = nullptr;
+    }
   }
   return run_generic(g, p.dtype, s);
+}
+
+}  // namespace
+
+int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, int64_t* maxs,
+                     uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                     const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
+                     double* spectral_acc, void* workspace, cudaStream_t s) {
+  return fused_bip_impl("dm_fused_bip", p, plane, nullptr, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
+                        lut_z, cap_z, err8_z, hist8_z, want_sam, spectral_acc, workspace, s);
+}
+
+int launch_fused_bip_scan(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts,
+                          int64_t* sums, int64_t* maxs,
+                          uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                          const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
+                          double* spectral_acc, void* workspace, cudaStream_t s) {
+  const ScanSpec sc{valid_in, plane_out, counts};
+  return fused_bip_impl("dm_fused_bip_scan", p, nullptr, &sc, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
+                        lut_z, cap_z, err8_z, hist8_z, want_sam, spectral_acc, workspace, s);
 }
 
 // full 64-pixel tiles of a 180-band, 16-bit BIP pair through validity_ct_kernel; returns the number of

@@ -107,6 +107,17 @@ int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
                           hist8_z, want_sam, spectral_acc, workspace, static_cast<cudaStream_t>(stream));
 }
 
+int dm_fused_bip_scan(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts_out,
+                      int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
+                      const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z,
+                      int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, int32_t want_sam, double* spectral_acc,
+                      void* workspace, void* stream) {
+  if (!p) return fail(DM_EARG, "dm_fused_bip_scan: null pair");
+  return launch_fused_bip_scan(*p, valid_in, plane_out, counts_out, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
+                               lut_z, cap_z, err8_z, hist8_z, want_sam, spectral_acc, workspace,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int dm_fused_bsq(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g, const uint8_t* lut_z,
                  int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z, void* stream) {

@@ -228,6 +228,7 @@ class Want:
     ssim_gauss: bool = False
     generic_stats: bool = False   # force the scalar cross-check kernel
     fused: bool = True            # allow the one-pass BIP kernel (dm_fused_bip) when it applies
+    fused_scan: bool = True       # allow its validity-folding build (dm_fused_bip_scan: nodata / caller mask, ONE read)
 
 
 @dataclass
@@ -600,12 +601,21 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
     st = _stream_ptr()
     P = out if out is not None else Partials.allocate(pair.bands, want.hist_bins, dev, pair.np_dtype)
     cp = pair.c_pair()
-    if plane is None and needs_plane(pair, valid):
-        plane = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
-        check(L.dm_validity(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), st))
-        P.planes["valid"] = plane
     cap_g, cap_z = want.err8_caps
     want_planes = want.errmax or cap_g is not None or cap_z is not None
+    # the one-pass BIP kernel applies (see below); with a nodata value or a caller mask and EnMAP's 180 bands its
+    # validity-folding build reads the pair ONCE where dm_validity + dm_fused_bip read it twice
+    bip_one_pass = (want.stats and (want.moments or pair.bands == 180) and not want.hist_bins and not want.generic_stats
+                    and not want.sid and (want_planes or want.sam or pair.bands == 180) and pair.layout == "bip"
+                    and want.fused)
+    scan = (plane is None and needs_plane(pair, valid) and metrics_mask and bip_one_pass and want.fused_scan
+            and pair.bands == 180 and pair.npix >= 64 and pair.np_dtype in ("uint16", "int16")
+            and (valid is None or valid.data_ptr() % 16 == 0))
+    if plane is None and needs_plane(pair, valid):
+        plane = torch.empty(pair.npix, dtype=torch.uint8, device=dev)
+        if not scan:
+            check(L.dm_validity(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), st))
+        P.planes["valid"] = plane
     use = plane if (plane is not None and metrics_mask) else None
     lut_g = lut_z = None
     pl_e = pl_g = pl_z = None               # the planes THIS call writes (P may carry planes of an earlier call)
@@ -623,12 +633,20 @@ def evaluate(pair: DevicePair, want: Want, valid: Optional[torch.Tensor] = None,
                      _ptr(lut_g), 0 if lut_g is None else lut_g.numel() - 1, _ptr(pl_g), _ptr(P.hist8_g),
                      _ptr(lut_z), 0 if lut_z is None else lut_z.numel() - 1, _ptr(pl_z), _ptr(P.hist8_z))
     done_stats = done_spectral = False
+    if scan:
+        rc = L.dm_fused_bip_scan(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), _ptr(P.sums), _ptr(P.imax),
+                                 *spectral_args, 1 if want.sam else 0, _ptr(P.spec), _ptr(ws), st)
+        if rc == _lib.DM_OK:
+            done_stats = done_spectral = True
+            P.used_mask = True
+        elif rc == _lib.DM_EUNSUPPORTED:
+            check(L.dm_validity(C.byref(cp), _ptr(valid), _ptr(plane), _ptr(P.counts), st))
+        else:
+            check(rc)
     # one-pass BIP kernel: stats + error planes + SAM from a single read (the plane selects METRICS
     # pixels for the stats and QUICKLOOK / SPECTRAL pixels for the rest, so it needs use == plane)
     # (for EnMAP's 180 bands it is also the fastest stats-only kernel: its pixel warps then idle)
-    if (want.stats and (want.moments or pair.bands == 180) and not want.hist_bins and not want.generic_stats
-            and not want.sid and (want_planes or want.sam or pair.bands == 180) and pair.layout == "bip"
-            and use is plane and want.fused):
+    if bip_one_pass and use is plane and not done_stats:
         rc = L.dm_fused_bip(C.byref(cp), _ptr(plane), _ptr(P.sums), _ptr(P.imax), *spectral_args,
                             1 if want.sam else 0, _ptr(P.spec), _ptr(ws), st)
         if rc == _lib.DM_OK:

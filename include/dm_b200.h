@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 8
+#define DM_ABI_VERSION 9
 
 /* status codes */
 enum { DM_OK = 0, DM_EARG = 1, DM_ECUDA = 2, DM_EUNSUPPORTED = 3 };
@@ -188,6 +188,24 @@ int dm_fused_bip(const dm_pair_t* p, const uint8_t* plane, int64_t* sums, int64_
                  const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
                  const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
                  int32_t want_sam, double* spectral_acc, void* workspace, void* stream);
+
+/* The same one-pass kernel with the VALIDITY RULE FOLDED IN (ABI 9): for pairs whose files carry a nodata value
+ * (the real EnMAP products: int16, nodata -32768 in both files) and / or a caller mask, dm_validity + dm_fused_bip
+ * read the pair twice; here the pixel warps that serve a tile first sweep it for the three rules of dm_validity
+ * (run_codec.py:249-263, quicklooks.py:35-45, run_codec.py:314-319), hand the tile's validity bytes to the band
+ * warps through shared memory and only then start their own spectral sweep -- one read of the pair.
+ * valid_in (uint8, nonzero = valid, 16-byte aligned) may be NULL; plane_out (may be NULL when rows*width is a
+ * multiple of 64) receives the plane exactly as dm_validity writes it, for the kernels that follow (dm_spectral's
+ * SID, dm_sobel_lmse take it as `plane`); counts_out (3 x int64, accumulated, may be NULL) the pixels per bit.
+ * The reference's all-False-mask rule (run_codec.py:264: no valid pixel -> every pixel counts) is the caller's:
+ * counts_out[0] == 0 after the launch means "zero the statistics and rerun dm_fused_bip with plane = NULL".
+ * 180-band DM_BIP cubes of at least 64 pixels only; anything else returns DM_EUNSUPPORTED and the caller runs
+ * dm_validity + dm_fused_bip.  Everything else as dm_fused_bip. */
+int dm_fused_bip_scan(const dm_pair_t* p, const uint8_t* valid_in, uint8_t* plane_out, int64_t* counts_out,
+                      int64_t* sums, int64_t* maxs, uint16_t* errmax_out,
+                      const uint8_t* lut_g, int32_t cap_g, uint8_t* err8_g, int64_t* hist8_g,
+                      const uint8_t* lut_z, int32_t cap_z, uint8_t* err8_z, int64_t* hist8_z,
+                      int32_t want_sam, double* spectral_acc, void* workspace, void* stream);
 
 /* one-pass BSQ kernel for few-band cubes (Sentinel-2 Case A): dm_fused_stats (moments, no histogram)
  * + the error planes of dm_spectral from a SINGLE read -- a thread loads the same 8-pixel vector of

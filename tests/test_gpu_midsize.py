@@ -333,3 +333,87 @@ def test_sid_sam_every_lane_grouping_vs_oracle(lanes):
                     assert _close(got[k], want[k]), (lanes, bands, dtype, v is not None, k, got[k], want[k])
     finally:
         lib().dm_spectral_lanes_per_pixel(0)
+
+
+def _scan_pair(dtype, H, W, ref_nd, tst_nd, seed):
+    """A 180-band BIP pair whose files carry nodata values: whole invalid pixels (shared and one-sided), single-band
+    hits in either cube (METRICS drops the pixel, the dataset mask keeps it), hits on band 1 (QUICKLOOK rule)."""
+    from image_compression_analysis_b200 import synth
+    ref, dec = synth.case_b_pair(seed=seed, bands=180, height=H, width=W, amp=3, dtype=dtype, layout="bsq")
+    rng = np.random.default_rng(seed + 1)
+    both = rng.random((H, W)) < 0.06
+    if ref_nd is not None:
+        ref = synth.plant_nodata(ref, ref_nd, both | (rng.random((H, W)) < 0.01), extra_hits=150, seed=seed + 2)
+        ref[0, rng.integers(0, H, 40), rng.integers(0, W, 40)] = ref_nd
+    if tst_nd is not None:
+        dec = synth.plant_nodata(dec, tst_nd, both | (rng.random((H, W)) < 0.01), extra_hits=150, seed=seed + 3)
+        dec[0, rng.integers(0, H, 40), rng.integers(0, W, 40)] = tst_nd
+    return _bip(ref), _bip(dec)
+
+
+@pytest.mark.parametrize("variant", [0, 12, 23])
+@pytest.mark.parametrize("case", ["i16_both", "u16_ref_only", "u16_tst_only_mask", "i16_tail_planes", "u16_mixed_planes"])
+def test_validity_folding_one_pass_kernel_equals_validity_plus_masked_kernel(case, variant):
+    """dm_fused_bip_scan (validity computed by the pixel warps inside the one-pass kernel: ONE read of the pair)
+    against dm_validity + dm_fused_bip (two reads): the validity plane, the three counts, every integer partial, the
+    SAM sum and the ERR8 planes / histograms must be IDENTICAL -- same rule (run_codec.py:249-263, quicklooks.py:35-45,
+    run_codec.py:314-319), same arithmetic, same reduction order.  1 184+ tiles on 148 CTAs, so every stage of the
+    ring is reused behind the mask barrier; both builds of the kernel; a partial last tile; a caller mask."""
+    import torch
+    from image_compression_analysis_b200 import synth
+    from image_compression_analysis_b200._lib import lib
+    from image_compression_analysis_b200.engine import DevicePair, Want, evaluate, to_device
+    dtype, H, W, rnd, tnd, use_valid, planes = {
+        "i16_both": ("int16", 296, 256, -32768, -32768, False, False),
+        "u16_ref_only": ("uint16", 296, 256, 0, None, False, False),
+        "u16_tst_only_mask": ("uint16", 300, 256, None, 65535, True, False),
+        "i16_tail_planes": ("int16", 211, 173, -32768, -32768, True, True),      # 36 503 pixels = 570 tiles + 23
+        "u16_mixed_planes": ("uint16", 296, 256, 0, 7, False, True),
+    }[case]
+    r, d = _scan_pair(dtype, H, W, rnd, tnd, seed=31)
+    if tnd == 7:
+        d[d == 0] = 1                       # 0 is only the ORIGINAL's nodata here
+    pair = DevicePair.from_arrays(r, d, "bip", rnd, tnd)
+    valid = to_device(synth.random_valid_mask(9, H, W, 0.25).reshape(-1)) if use_valid else None
+    want = Want(stats=True, sam=True, err8_caps=(255, 32) if planes else (None, None), errmax=planes)
+    L = lib()
+    assert L.dm_fused_bip_variant(variant) == 0
+    try:
+        one = evaluate(pair, want, valid)
+        two = evaluate(pair, Want(**{**want.__dict__, "fused_scan": False}), valid)
+        torch.cuda.synchronize()
+    finally:
+        L.dm_fused_bip_variant(0)
+    assert one.used_mask and two.used_mask
+    a, b = one.to_host(), two.to_host()
+    assert np.array_equal(one.planes["valid"].cpu().numpy(), two.planes["valid"].cpu().numpy())
+    assert np.array_equal(a.counts, b.counts) and 0 < int(a.counts[0]) < int(a.counts[2]) <= H * W
+    assert np.array_equal(a.isum, b.isum)
+    assert np.array_equal(a.imax, b.imax)
+    assert np.array_equal(a.fsum, b.fsum)                       # SAM: same pixels, same order, same bits
+    for k in ("errmax", "err8_g", "err8_z") if planes else ():
+        assert np.array_equal(one.planes[k].cpu().numpy(), two.planes[k].cpu().numpy()), k
+
+
+def test_validity_folding_kernel_vs_oracle_and_all_false_rule():
+    """The one-read route end to end through the public mirror (compute_metrics_arrays takes it by itself for a
+    180-band BIP pair with nodata) against the ORACLE, stats-only (the pixel warps then only scan) and with SAM; and
+    run_codec.py:264: when NO pixel is valid the statistics are those of every pixel (counts come back 0, the host
+    reruns unmasked)."""
+    import image_compression_analysis_b200 as dm
+    from oracle import distortion_oracle as orc
+    r, d = _scan_pair("int16", 148, 128, -32768, -32768, seed=41)
+    rb, db = np.ascontiguousarray(np.moveaxis(r, -1, 0)), np.ascontiguousarray(np.moveaxis(d, -1, 0))
+    kw = dict(ref_nodata=-32768, tst_nodata=-32768)
+    want = orc.compute_metrics(rb, db, None, extras=False, **kw)
+    _check(dm.compute_metrics_arrays(r, d, layout="bip", **kw), want)
+    want.update(orc.compute_sam_sid_lmse_caseB(rb, db, None, **kw))
+    _check(dm.all_metrics_arrays(r, d, layout="bip", case_b=True, extras=False, **kw), want)
+    # every pixel carries one nodata sample somewhere: METRICS selects nothing -> everything counts
+    r2 = r.copy()
+    rng = np.random.default_rng(5)
+    r2.reshape(-1, 180)[np.arange(148 * 128), rng.integers(1, 180, 148 * 128)] = -32768
+    rb2 = np.ascontiguousarray(np.moveaxis(r2, -1, 0))
+    want = orc.compute_metrics(rb2, db, None, extras=False, **kw)
+    got = dm.compute_metrics_arrays(r2, d, layout="bip", **kw)
+    _check(got, want)
