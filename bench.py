@@ -542,6 +542,58 @@ def run_configs(torch, dist, world, rank, local, peak, clocks_mhz):
     }
     if comb5 is not None:
         comb5.close()
+
+    # ---- C2r: the REAL EnMAP configuration of configs[1]: int16 samples, nodata -32768 in both files ------------
+    # (tools/make_baseline_B.py:302-312 writes that; mask rule run_codec.py:249-263).  A no-data corner (a triangle,
+    # 5 % of the pixels: EnMAP tiles are cut from a rotated swath) in the original and the decoded cubes; per GPU three
+    # decoded cubes of this rank's share of the sweep against the one original, rotated (> L2).  One launch per pair:
+    # the validity rule is evaluated inside the one-pass kernel (dm_fused_bip_scan), the pair is read ONCE.
+    yy = torch.arange(Hb, device=dev).view(Hb, 1)
+    xx = torch.arange(Wb, device=dev).view(1, Wb)
+    corner = (yy + xx) < int((2 * 0.05 * Hb * Wb) ** 0.5)
+    n_corner = int(corner.sum().item())
+    orig_r = orig.clone()
+    orig_r[corner] = -32768
+    ids_r = mine[:3]
+    for i in ids_r:
+        decs[i][corner] = -32768
+    run_r, outs_r = Partials.allocate_run(64, Bb, 0, dev, "int16")
+    pairs_r = [DevicePair(orig_r, decs[i], "int16", "bip", Bb, Hb, Wb, -32768, -32768) for i in ids_r]
+    one_r = [PreparedFused(pairs_r[k % len(pairs_r)], Want(stats=True, sam=True), outs_r[k], scan=True) for k in range(64)]
+    plane_r = torch.empty(Hb * Wb, dtype=torch.uint8, device=dev)
+    two_out = Partials.allocate(Bb, 0, dev, "int16")
+
+    def two_reads(k):
+        evaluate(pairs_r[k % len(pairs_r)], Want(stats=True, sam=True, fused_scan=False), out=two_out)
+
+    def sweep_r():
+        run_r.zero_()
+        for pf in one_r:
+            pf.launch(chain=True)
+
+    sweep_r()
+    two_reads(0)
+    torch.cuda.synchronize()
+    hr, h2 = outs_r[0].to_host(), two_out.to_host()
+    assert int(hr.counts[0]) == Hb * Wb - n_corner and int(hr.sums[0, 0]) == Hb * Wb - n_corner, (hr.counts, n_corner)
+    assert np.array_equal(hr.isum, h2.isum) and np.array_equal(hr.imax, h2.imax) and np.array_equal(hr.fsum, h2.fsum), \
+        "one-read route != dm_validity + dm_fused_bip"
+    ms_r, _ = timed(sweep_r, 3, warm=1)
+    ms_r /= len(one_r)
+    ms_2, nl_2 = timed(lambda: [two_reads(k) for k in range(6)], 3, warm=1)
+    ms_2 /= 6
+    out["C2r_caseB_int16_nodata_one_read"] = {
+        "workload": "configs[1] as the real EnMAP product: 1024x1024x180 int16 BIP cube pair per GPU with nodata -32768 in both "
+                    "files (a no-data corner, 5 % of the pixels): compute_metrics (run_codec.py:249-304 mask rule included) + SAM",
+        "scaling": "weak", "pairs_per_gpu_rotated": len(pairs_r), "launches_per_pair": 1,
+        "api": "engine.PreparedFused(scan=True) -> dm_fused_bip_scan: validity evaluated by the kernel's pixel warps, pair read once",
+        "us_per_pair": ms_r * 1e3, "GBps": world * pair_bytes / ms_r / 1e6,
+        "two_reads_us_per_pair": ms_2 * 1e3, "two_reads_launches_per_pair": int(nl_2) // 6,
+        "two_reads_api": "evaluate(fused_scan=False): dm_validity + dm_fused_bip (r01 path)",
+        "roofline": roof(world * pair_bytes, ms_r, "hbm"),
+        "checked": "counts, every integer partial and the SAM sum bit-identical to the two-read route on this rank's first pair",
+    }
+    del one_r, pairs_r, run_r, outs_r, orig_r, plane_r, two_out
     return out
 
 

@@ -458,18 +458,30 @@ class PreparedFused:
     For sweeps that evaluate thousands of pairs, where the per-call Python work of `evaluate` (a few
     tens of microseconds) would otherwise rival the 150 us kernel when several ranks share a host."""
 
-    def __init__(self, pair: DevicePair, want: Want, out: "Partials", plane: Optional[torch.Tensor] = None):
+    def __init__(self, pair: DevicePair, want: Want, out: "Partials", plane: Optional[torch.Tensor] = None,
+                 scan: bool = False, valid: Optional[torch.Tensor] = None, plane_out: Optional[torch.Tensor] = None):
+        """plane: a validity plane computed earlier (dm_validity).  scan=True instead: the pair carries nodata values
+        and / or `valid` is the caller's mask, and the kernel derives the validity itself while it reads the pair
+        (dm_fused_bip_scan, 180-band cubes; counts land in out.counts, the plane in plane_out when given).  The
+        reference's all-False-mask rule (run_codec.py:264) is the caller's to apply on out.counts[0]."""
         if pair.layout != "bip" or want.hist_bins or want.sid or want.lmse or want.ssim_gauss or want.errmax \
                 or want.err8_caps != (None, None) or not want.stats:
             raise ValueError("PreparedFused covers stats (+ SAM) on BIP cubes; use evaluate() for the rest")
-        self._keep = (pair, out, plane, workspace(pair.ref.device) if want.sam else None)
+        if scan and (plane is not None or pair.bands != 180 or (plane_out is None and pair.npix % 64)):
+            raise ValueError("scan=True: 180-band cubes, no precomputed plane, plane_out unless rows*width % 64 == 0")
+        self._keep = (pair, out, plane, workspace(pair.ref.device) if want.sam else None, valid, plane_out)
         self._cp = pair.c_pair()
-        self._fn = lib().dm_fused_bip
         self._chain = lib().dm_launch_chaining
         ws = self._keep[3]
-        self._args = (C.byref(self._cp), _ptr(plane), _ptr(out.sums), _ptr(out.imax), None, None, 0, None, None,
-                      None, 0, None, None, 1 if want.sam else 0, _ptr(out.spec), _ptr(ws), _stream_ptr())
-        out.used_mask = plane is not None
+        tail = (_ptr(out.sums), _ptr(out.imax), None, None, 0, None, None,
+                None, 0, None, None, 1 if want.sam else 0, _ptr(out.spec), _ptr(ws), _stream_ptr())
+        if scan:
+            self._fn = lib().dm_fused_bip_scan
+            self._args = (C.byref(self._cp), _ptr(valid), _ptr(plane_out), _ptr(out.counts), *tail)
+        else:
+            self._fn = lib().dm_fused_bip
+            self._args = (C.byref(self._cp), _ptr(plane), *tail)
+        out.used_mask = plane is not None or scan
 
     def launch(self, chain: bool = True) -> None:
         """chain=True: this launch may start while the previous kernel on the stream drains (programmatic
