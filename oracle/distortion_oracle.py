@@ -23,13 +23,16 @@ Pinning status
   by the real reference with oracle/make_golden.py for the GPU box.
 * MAE / histograms: defined on the reference's own `diff_i32`
   (run_codec.py:275); trivially pinned by that definition.
-* Gaussian SSIM: PARITY UNPINNED.  The reference has no windowed SSIM and
-  scikit-image is not installed here; the definition below restates
+* Gaussian SSIM: PARITY UNPINNED AGAINST SCIKIT-IMAGE (it is not installed
+  here, and the reference has no windowed SSIM of its own); pinned instead on
+  a third-party computation: tests/golden/ssimw_cv2.npz holds values obtained
+  with OpenCV's GaussianBlur(11 x 11, sigma 1.5) -- the formulation of OpenCV's
+  own SSIM sample -- plus skimage's 5-px crop (oracle/make_golden_ssim_cv2.py),
+  and both statements below agree with them to 1e-15.  The definition restates
   skimage.metrics.structural_similarity(gaussian_weights=True, sigma=1.5,
-  use_sample_covariance=False) on top of scipy.ndimage.gaussian_filter.
+  use_sample_covariance=False) on top of scipy.ndimage.gaussian_filter;
   ssim_gaussian_band_direct() states the same quantity a second time from the
-  SSIM paper's definition (direct 11 x 11 window sums, no scipy) so that the
-  pin does not rest on one restatement; it is still not skimage itself.
+  SSIM paper's definition (direct 11 x 11 window sums, no scipy).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
 arm may import this module.  It is the checker, never the product: the product
@@ -392,7 +395,7 @@ def error_max8(ref: np.ndarray, tst: np.ndarray, err_max_global: Optional[int] =
 
 
 # --------------------------------------------------------------------------
-# Gaussian-window SSIM (addition x1; PARITY UNPINNED, see header)
+# Gaussian-window SSIM (addition x1; pinned on OpenCV-computed fixtures, not on skimage itself: see header)
 # --------------------------------------------------------------------------
 
 SSIMW_SIGMA = 1.5

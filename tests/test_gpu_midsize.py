@@ -417,3 +417,22 @@ def test_validity_folding_kernel_vs_oracle_and_all_false_rule():
     want = orc.compute_metrics(rb2, db, None, extras=False, **kw)
     got = dm.compute_metrics_arrays(r2, d, layout="bip", **kw)
     _check(got, want)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_gaussian_ssim_kernels_vs_opencv_fixtures(variant):
+    """Every build of the Gaussian-SSIM kernel against the OpenCV-computed fixtures (tests/golden/ssimw_cv2.npz,
+    oracle/make_golden_ssim_cv2.py): a filter implementation that shares nothing with scipy or this repository."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200._lib import lib
+    z = np.load(ROOT / "tests" / "golden" / "ssimw_cv2.npz")
+    L_ = lib()
+    if L_.dm_ssim_variant(variant) != 0:
+        pytest.skip(f"dm_ssim_variant({variant}) not offered by this build")
+    try:
+        for n in sorted({k.split("__")[0] for k in z.files}):
+            a, b, L, want = z[n + "__a"], z[n + "__b"], float(z[n + "__L"]), float(z[n + "__ssim"])
+            got = dm.ssim_gaussian_arrays(a[None], b[None], L)["ssimw_b1"]
+            assert _close(got, want), (n, got, want)
+    finally:
+        L_.dm_ssim_variant(0)

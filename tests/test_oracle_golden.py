@@ -1,5 +1,6 @@
 """CPU: the numpy oracle (oracle/distortion_oracle.py) against the reference-generated goldens."""
 import math
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -88,3 +89,34 @@ def test_two_independent_gaussian_ssim_statements_agree(dtype, L, amp):
     s2 = orc.ssim_gaussian_band_direct(a, b, L)
     assert abs(s1 - s2) <= 1e-11 * max(1.0, abs(s1)), (s1, s2)
     assert orc.ssim_gaussian_band_direct(a, a, L) == pytest.approx(1.0, abs=1e-12)
+
+
+def _cv2_fixture():
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ssimw_cv2.npz")
+    for n in sorted({k.split("__")[0] for k in z.files}):
+        yield n, z[n + "__a"], z[n + "__b"], float(z[n + "__L"]), float(z[n + "__ssim"])
+
+
+def test_gaussian_ssim_oracle_pinned_on_opencv_fixtures():
+    """Third-party pin of the one metric the reference does not have: both oracle statements of the Gaussian-window
+    SSIM against values computed with OpenCV's GaussianBlur(11 x 11, sigma 1.5) (oracle/make_golden_ssim_cv2.py,
+    the formulation of OpenCV's own SSIM sample + skimage's 5-px crop).  Observed agreement 1e-15; bar 1e-12."""
+    from oracle import distortion_oracle as orc
+    n_cases = 0
+    for name, a, b, L, want in _cv2_fixture():
+        assert orc.ssim_gaussian_band(a, b, L) == pytest.approx(want, rel=1e-12), name
+        assert orc.ssim_gaussian_band_direct(a, b, L) == pytest.approx(want, rel=1e-12), name
+        n_cases += 1
+    assert n_cases == 5
+
+
+def test_opencv_fixtures_reproduce_when_opencv_is_installed():
+    """The committed fixture is what OpenCV says today (skipped where cv2 is missing)."""
+    pytest.importorskip("cv2")
+    from oracle import make_golden_ssim_cv2 as mk
+    for name, a, b, L, want in _cv2_fixture():
+        assert mk.ssim_cv2(a, b, L) == pytest.approx(want, rel=1e-13), name
+    for name, dtype, shape, L, amp, seed in mk.CASES:
+        a, b = mk.make_pair(dtype, shape, amp, seed)
+        fa = [x for x in _cv2_fixture() if x[0] == name][0]
+        assert np.array_equal(a, fa[1]) and np.array_equal(b, fa[2]), name
