@@ -11,7 +11,11 @@ B, H, W = 180, 1024, 1024
 g = torch.Generator(device="cuda").manual_seed(3)
 ref = (torch.randint(0, 2500, (H, W, B), device="cuda", dtype=torch.int16, generator=g) * 4)
 frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.05
-bad = torch.rand((H, W), device="cuda", generator=g) < frac
+if len(sys.argv) > 2 and sys.argv[2] == "corner":      # a no-data corner (EnMAP tiles are cut from a rotated swath)
+    yy = torch.arange(H, device="cuda").view(H, 1); xx = torch.arange(W, device="cuda").view(1, W)
+    bad = (yy + xx) < int((2 * frac * H * W) ** 0.5)
+else:                                                  # scattered single pixels (the adverse case: every warp meets one)
+    bad = torch.rand((H, W), device="cuda", generator=g) < frac
 ref[bad] = -32768
 tst = (ref + torch.randint(-3, 4, (H, W, B), device="cuda", dtype=torch.int16, generator=g)).clamp_(-32768, 32767)
 tst[bad] = -32768
@@ -43,7 +47,7 @@ def args(sam, err):
     return (_ptr(P.sums), _ptr(P.imax), None, None, 0, None, None, None, 0, None, None, sam, _ptr(P.spec), _ptr(ws), _stream_ptr())
 
 
-print(f"invalid pixels: {frac:.0%}")
+print(f"invalid pixels: {frac:.0%} ({sys.argv[2] if len(sys.argv) > 2 else 'scattered'})")
 for variant in (12, 23):
     L.dm_fused_bip_variant(variant)
     for wn, sam, err in (("stats", 0, False), ("stats+sam", 1, False), ("stats+sam+err8", 1, True)):
