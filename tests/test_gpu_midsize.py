@@ -436,3 +436,42 @@ def test_gaussian_ssim_kernels_vs_opencv_fixtures(variant):
             assert _close(got, want), (n, got, want)
     finally:
         L_.dm_ssim_variant(0)
+
+
+def test_sid_gain_errors_dark_spectra_and_mixtures_vs_oracle():
+    """SID on error patterns the synthetic codec noise does not produce: pure gain errors of 1 % and 20 % (the SID of
+    such a pair is rounding noise, ~1e-8, under per-pixel sums of 1e-2: any formulation that lets sum d^2/s meet
+    (sum d)^2 cancels here -- the kernel's one-exact-numerator form does not; an r02 experiment that did, 5 FP64
+    operations per sample instead of 18, was no faster because the kernel is issue bound, and was dropped), dark noisy
+    spectra (most samples on the log() list), an image that mixes them pixel by pixel, identical cubes (exactly 0)."""
+    import image_compression_analysis_b200 as dm
+    from image_compression_analysis_b200._lib import check, lib
+    from oracle import distortion_oracle as orc
+    rng = np.random.default_rng(77)
+    B, H, W = 180, 40, 64
+    base = (rng.integers(0, 2500, (B, H, W)) * 4).astype(np.int64)
+    noise = base + rng.integers(-3, 4, base.shape)
+    gain1 = np.rint(base * 0.99).astype(np.int64)
+    gain20 = np.rint(base * 1.2).astype(np.int64)
+    dark = rng.integers(0, 30, (B, H, W)).astype(np.int64)
+    dark_n = dark + rng.integers(-3, 4, dark.shape)
+    mixed_r = base.copy()
+    mixed_d = noise.copy()
+    odd = (np.arange(H * W).reshape(H, W) % 3) == 1
+    mixed_d[:, odd] = gain1[:, odd]
+    mixed_r[:, 5:9, :] = dark[:, 5:9, :]; mixed_d[:, 5:9, :] = dark_n[:, 5:9, :]
+    cases = {"noise": (base, noise, 1e-9), "gain 0.99": (base, gain1, REL), "gain 1.2": (base, gain20, REL),
+             "dark": (dark, dark_n, 1e-9), "mixed": (mixed_r, mixed_d, 1e-8), "identical": (base, base, 0.0)}
+    for lanes in (16, 8, 32):
+        check(lib().dm_spectral_lanes_per_pixel(lanes))
+        try:
+            for name, (r, d, rel) in cases.items():
+                r16, d16 = np.clip(r, 0, 65535).astype(np.uint16), np.clip(d, 0, 65535).astype(np.uint16)
+                want = orc.compute_sam_sid_lmse_caseB(r16, d16)["sid"]
+                got = dm.compute_sam_sid_lmse_caseB_arrays(_bip(r16), _bip(d16), layout="bip")["sid"]
+                if name == "identical":
+                    assert got == 0.0 and want == 0.0
+                else:
+                    assert abs(got - want) <= rel * abs(want), (lanes, name, got, want, abs(got - want) / abs(want))
+        finally:
+            lib().dm_spectral_lanes_per_pixel(0)
