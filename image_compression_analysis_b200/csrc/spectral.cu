@@ -302,8 +302,18 @@ __device__ __forceinline__ long long group_add_ll(long long v) {
   for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ double splice_u32(int v) {      // exact int -> float64 for 0 <= v < 2^31 (one subtraction)
+// exact int -> float64 for 0 <= v < 2^31.  r02 (late): the conversion instruction again.  The 2^52 mantissa splice
+// (__hiloint2double(0x43300000, v) - 2^52) saves an FP64-pipe slot per conversion but costs two register moves to
+// pair the sample with the constant high word (IMAD.MOV was 10 % of the executed instructions, profiles/
+// r02i_ncu_sid_16_lanes.txt), and the kernel is bound by issue slots (66 %), not by the FP64 pipe (44 %): I2F.F64 is
+// one issue slot.  Measured on the Case-B cube: SID 565 -> 494 us with 8 lanes per pixel (whose 12 words per lane no
+// longer spill), 518 -> 507 us with 16; results bit-identical.  -DDM_SPLICE_I2D brings the splice back.
+__device__ __forceinline__ double splice_u32(int v) {
+#ifdef DM_SPLICE_I2D
   return __hiloint2double(0x43300000, v) - 4503599627370496.0;
+#else
+  return (double)v;
+#endif
 }
 
 __device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -526,9 +536,9 @@ int launch_spectral(const dm_pair_t& p, const uint8_t* plane, uint16_t* errmax_o
     // then 16, then the whole warp
     const int wpx = (int)(p.bands / 2);
     int lpp = spectral_lanes_per_pixel();                                // dm_spectral_lanes_per_pixel(): 0 = auto
-    // measured on the Case-B cube (r02e): SID 627 / 510 / 509 us and SAM + SID 760 / 674 / 832 us with 8 / 16 / 32 lanes
-    // per pixel (8 lanes need 12 words per lane for 180 bands and spill at 128 registers)
-    if (lpp == 0) lpp = wpx <= 8 * 6 ? 8 : (wpx <= 16 * 8 ? 16 : 32);
+    // measured on the Case-B cube: SID 494 / 507 / 506 us and SAM + SID 581 / 653 / 769 us with 8 / 16 / 32 lanes per pixel
+    // (r02e, with the mantissa splice and 12 spilling words per lane at 8 lanes: 627 / 510 / 509 and 760 / 674 / 832)
+    if (lpp == 0) lpp = wpx <= 8 * 12 ? 8 : (wpx <= 16 * 8 ? 16 : 32);
     if ((lpp == 8 && wpx > 8 * 12) || (lpp == 16 && wpx > 16 * 8)) lpp = 32;
 #define DM_SPEC16(DT)                                                                                   \
     do {                                                                                                \

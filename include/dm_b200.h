@@ -158,7 +158,7 @@ int dm_spectral(const dm_pair_t* p, const uint8_t* plane,
                 int32_t want_sam, int32_t want_sid, double* spectral_acc, void* workspace, void* stream);
 
 /* lanes that share one pixel in the register-resident SAM / SID kernel of dm_spectral (16-bit BIP cubes, no planes):
- * 0 = by band count (8 lanes up to 96 bands, 16 up to 256 -- two pixels per warp for EnMAP's 180 --, else 32),
+ * 0 = by band count (8 lanes up to 192 bands -- four pixels per warp for EnMAP's 180 --, 16 up to 256, else 32),
  * 8 / 16 / 32 = pin (a choice the band count does not fit falls back to 32).  Thread-local; for A/B measurements
  * and the parity tests, which cover every grouping. */
 int dm_spectral_lanes_per_pixel(int32_t lanes);
