@@ -529,7 +529,11 @@ class PreparedCaseAAll:
     full   the resident rows including the halo the SSIM window needs; rows = counted rows in buffer coordinates"""
 
     def __init__(self, core: DevicePair, full: DevicePair, rows: Tuple[int, int], out: "Partials", data_range: float,
-                 err8_caps=(255, 32), hist_bins: int = 256):
+                 err8_caps=(255, 32), hist_bins: int = 256, side_stream: Optional["torch.cuda.Stream"] = None):
+        """side_stream: run the two HBM-bound passes (statistics + planes, histograms) there, BEHIND the FP64-bound SSIM
+        kernel that is issued first on the current stream: the three kernels write disjoint outputs, so the short
+        passes run in the SSIM kernel's shadow (its blocks leave registers and shared memory for one more block per SM)
+        instead of in front of it; launch() forks and joins the side stream with events."""
         dev = core.ref.device
         L = lib()
         self._keep = (core, full, out)
@@ -539,13 +543,15 @@ class PreparedCaseAAll:
         lut_g, lut_z = _lut_on_device(err8_caps[0], dev), _lut_on_device(err8_caps[1], dev)
         self._luts = (lut_g, lut_z)
         st = _stream_ptr()
+        self._side = side_stream
+        st_hbm = C.c_void_p(side_stream.cuda_stream) if side_stream is not None else st
         self._ws = workspace(dev)
         self._a_bsq = (C.byref(self._cc), None, _ptr(out.sums), _ptr(out.imax), None,
                        _ptr(lut_g), lut_g.numel() - 1, _ptr(self.planes["err8_g"]), _ptr(out.hist8_g),
-                       _ptr(lut_z), lut_z.numel() - 1, _ptr(self.planes["err8_z"]), _ptr(out.hist8_z), st)
+                       _ptr(lut_z), lut_z.numel() - 1, _ptr(self.planes["err8_z"]), _ptr(out.hist8_z), st_hbm)
         self._junk = torch.zeros(2 * core.bands * DM_NSTAT, dtype=torch.int64, device=dev)
         self._a_hist = (C.byref(self._cc), None, DM_VALID_METRICS, hist_bins, _lib.DM_STATS_NO_MOMENTS, _ptr(self._junk),
-                        _ptr(self._junk[core.bands * DM_NSTAT:]), _ptr(out.hist), st)
+                        _ptr(self._junk[core.bands * DM_NSTAT:]), _ptr(out.hist), st_hbm)
         self._scr = _scratch(dev, "ssim", full.bands * L.dm_ssim_nblocks() * 2)
         self._a_ssim = (C.byref(self._cf), float(data_range), rows[0], rows[1], full.img_row0, full.img_rows,
                         _ptr(self._scr), _ptr(out.ssimw_sum), _ptr(out.ssimw_cnt), _ptr(self._ws), st)
@@ -554,10 +560,23 @@ class PreparedCaseAAll:
 
     def launch(self) -> None:
         L = self._L
+        if self._side is None:
+            check(L.dm_fused_bsq(*self._a_bsq))
+            if self._hist_bins:
+                check(L.dm_fused_stats(*self._a_hist))
+            check(L.dm_ssim_gauss(*self._a_ssim))
+            return
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._side.wait_event(fork)
+        check(L.dm_ssim_gauss(*self._a_ssim))
         check(L.dm_fused_bsq(*self._a_bsq))
         if self._hist_bins:
             check(L.dm_fused_stats(*self._a_hist))
-        check(L.dm_ssim_gauss(*self._a_ssim))
+        join = torch.cuda.Event()
+        join.record(self._side)
+        cur.wait_event(join)
 
 
 class PreparedStatsBatch:

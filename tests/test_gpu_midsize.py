@@ -475,3 +475,38 @@ def test_sid_gain_errors_dark_spectra_and_mixtures_vs_oracle():
                     assert abs(got - want) <= rel * abs(want), (lanes, name, got, want, abs(got - want) / abs(want))
         finally:
             lib().dm_spectral_lanes_per_pixel(0)
+
+
+@pytest.mark.parametrize("side", [False, True])
+def test_prepared_case_a_all_vs_oracle(side):
+    """engine.PreparedCaseAAll (what bench.py's configs C3 / C4 launch): statistics + both ERR8 planes in one pass,
+    256-bin histograms and the Gaussian SSIM of a BSQ image from prepared arguments, with and without the side
+    stream that runs the two HBM-bound passes in the SSIM kernel's shadow -- against the oracle, launched twice into
+    the same vector (accumulation) and read back after a plain stream synchronisation."""
+    import torch
+    from image_compression_analysis_b200 import finish, synth, _lib
+    from image_compression_analysis_b200.engine import DevicePair, Partials, PreparedCaseAAll
+    from oracle import distortion_oracle as orc
+    ref, dec = synth.case_a_pair(seed=12, bands=4, height=300, width=408)
+    pair = DevicePair.from_arrays(ref, dec, "bsq")
+    P = Partials.allocate(4, 256, pair.ref.device, "uint16")
+    st = torch.cuda.Stream() if side else None
+    prep = PreparedCaseAAll(pair, pair, (0, 300), P, 4095.0, side_stream=st)
+    prep.launch()
+    torch.cuda.current_stream().synchronize()
+    h = P.to_host()
+    got = finish.finish_compute_metrics(_lib.DM_U16, h.sums, h.maxs)
+    _check(got, orc.compute_metrics(ref, dec, extras=False))
+    want = orc.compute_metrics(ref, dec, hist_bins=256)
+    for b in range(4):
+        assert np.array_equal(h.hist[b], want[f"hist_b{b+1}"]), b
+    sw = finish.finish_ssim_gauss(h.ssimw_sum, h.ssimw_cnt)
+    for k, w in orc.ssim_gaussian(ref, dec, 4095.0).items():
+        assert _close(sw[k], w), (k, sw[k], w)
+    e = orc.error_max8(ref, dec, 255, 32)
+    assert np.array_equal(prep.planes["err8_g"].cpu().numpy().reshape(300, 408), e["err8_g"])
+    assert np.array_equal(prep.planes["err8_z"].cpu().numpy().reshape(300, 408), e["err8_z"])
+    prep.launch()                                   # accumulates: every integer doubles
+    torch.cuda.current_stream().synchronize()
+    h2 = P.to_host()
+    assert np.array_equal(h2.sums, 2 * h.sums) and np.array_equal(h2.hist, 2 * h.hist)
