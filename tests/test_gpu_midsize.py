@@ -510,3 +510,33 @@ def test_prepared_case_a_all_vs_oracle(side):
     torch.cuda.current_stream().synchronize()
     h2 = P.to_host()
     assert np.array_equal(h2.sums, 2 * h.sums) and np.array_equal(h2.hist, 2 * h.hist)
+
+
+def test_validity_folding_kernel_is_repeatable_under_load():
+    """The in-kernel scan hands tiles from the pixel warps to the band warps through a third mbarrier per stage and
+    the band warps wait on that barrier alone: 40 launches on a full-size EnMAP-like int16 + nodata cube (16 384
+    tiles each, scattered single-band nodata hits so that both sweeps of the scan run) must give the same plane, counts
+    and integer partials every time, and the same as dm_validity + dm_fused_bip."""
+    import torch
+    from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
+    B, H, W = 180, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ref = torch.randint(0, 2500, (H, W, B), device="cuda", dtype=torch.int16, generator=g) * 4
+    tst = (ref + torch.randint(-3, 4, (H, W, B), device="cuda", dtype=torch.int16, generator=g)).clamp_(-32768, 32767)
+    bad = torch.rand((H, W), device="cuda", generator=g) < 0.03
+    ref[bad] = -32768
+    tst[bad] = -32768
+    hits = torch.randint(0, H * W * B, (5000,), device="cuda", generator=g)
+    ref.view(-1)[hits[:2500]] = -32768
+    tst.view(-1)[hits[2500:]] = -32768
+    pair = DevicePair(ref, tst, "int16", "bip", B, H, W, -32768, -32768)
+    two = evaluate(pair, Want(stats=True, sam=True, fused_scan=False))
+    want_plane = two.planes["valid"].clone()
+    t = two.to_host()
+    for i in range(40):
+        one = evaluate(pair, Want(stats=True, sam=True))
+        assert torch.equal(one.planes["valid"], want_plane), i
+        h = one.to_host()
+        assert np.array_equal(h.counts, t.counts) and np.array_equal(h.isum, t.isum) and np.array_equal(h.imax, t.imax) \
+            and np.array_equal(h.fsum, t.fsum), i
+    assert 0 < int(t.counts[0]) < int(t.counts[2]) < H * W
