@@ -603,6 +603,9 @@ __device__ __forceinline__ bool mbar_arrive_is_last_a(uint32_t bar) {
 // barrier; the band warps wait for THAT barrier instead of the full barrier, so they trail the data by the
 // scan only, not by the pixel group's whole SAM sweep, and the 4-stage ring keeps its slack.  One read of
 // the pair instead of two (validity pre-pass + masked kernel): run_codec.py:249-263 folded into :268-285.
+template <class T> __device__ __forceinline__ constexpr int stage_of(T) { return T::value; }     // std::integral_constant
+__device__ __forceinline__ constexpr int stage_of(int s) { return s; }
+
 template <int BANDS, int DT, bool MASK, bool ERR, int MPW, bool SCAN = false>
 __global__ void __launch_bounds__(Geo<BANDS, MPW>::THREADS, 1)
 fused_ct_kernel(FusedArgs g) {
@@ -734,72 +737,97 @@ fused_ct_kernel(FusedArgs g) {
     auto run = [&](auto nm_tag) {
       constexpr int NM = decltype(nm_tag)::value;
       constexpr int EPOCH = 128 / G::ROWBLOCKS;
-      for (int it0 = 0; it0 < my_tiles; it0 += EPOCH) {
-        const int it1 = it0 + EPOCH < my_tiles ? it0 + EPOCH : my_tiles;
-        for (int it = it0; it < it1; ++it) {
-          const int s = it & (kStages - 1);
-          // SCAN: the mask barrier completes after the pixel warps have seen the full barrier complete and released
-          // their writes, so it orders the tile's data as well (one wait per tile instead of two: -3 us)
-          if (SCAN) mbar_wait_a(mask0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
-          else mbar_wait_a(full0 + 8u * (uint32_t)s, (uint32_t)((it / kStages) & 1), poll_ns);
-          if (!(dbg & 2)) {
-            const uint32_t xs = ld_off + (uint32_t)s * G::PITCH;
-            const unsigned char* pl = smem + (size_t)s * G::PITCH + G::STAGE;      // MASK: the tile's validity bytes
+      static_assert(EPOCH % kStages == 0, "an epoch starts in stage 0");
+      // one tile in stage S
+      auto tile = [&](auto s_tag, int it, uint32_t par) {
+        // S: std::integral_constant (unrolled trips: offsets and barrier addresses fold into immediates) or a plain int
+        const int S = stage_of(s_tag);
+        // SCAN: the mask barrier completes after the pixel warps have seen the full barrier complete and released
+        // their writes, so it orders the tile's data as well (one wait per tile instead of two: -3 us)
+        mbar_wait_a((SCAN ? mask0 : full0) + 8u * (uint32_t)S, par, poll_ns);
+        if (!(dbg & 2)) {
+          const uint32_t xs = ld_off + (uint32_t)S * G::PITCH;
+          const unsigned char* pl = smem + (size_t)S * G::PITCH + G::STAGE;      // MASK: the tile's validity bytes
 #pragma unroll
-            for (int rb = 0; rb < G::ROWBLOCKS; ++rb) {
-              uint32_t xr[MPW], yr[MPW];
-              if constexpr (MPW == 4) {
-                ldsm_x4_trans(xr, xs + rb * (16 * G::PIXB));
-                ldsm_x4_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
-              } else {
-                ldsm_x2_trans(xr, xs + rb * (16 * G::PIXB));
-                ldsm_x2_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
-              }
-              uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
-              if (MASK) {
-                // pixels 16rb + 4r .. +3 of the tile: even/odd pixel of row 2r, even/odd pixel of row 2r+1
-                const uint32_t vb = *reinterpret_cast<const uint32_t*>(pl + 16 * rb + 4 * r);
-                m0 = ((vb & DM_VALID_METRICS) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 16)) ? 0xffff0000u : 0u);
-                m1 = ((vb & (DM_VALID_METRICS << 8)) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 24)) ? 0xffff0000u : 0u);
-                n0 += (m0 & 1u) + (m0 >> 31);
-                n1 += (m1 & 1u) + (m1 >> 31);
-              }
-              // data-range scan on the raw reference words (unmasked); a short last warp re-reads its
-              // last chunk in the unused matrices, which changes neither an OR nor a maximum
+          for (int rb = 0; rb < G::ROWBLOCKS; ++rb) {
+            uint32_t xr[MPW], yr[MPW];
+            if constexpr (MPW == 4) {
+              ldsm_x4_trans(xr, xs + rb * (16 * G::PIXB));
+              ldsm_x4_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+            } else {
+              ldsm_x2_trans(xr, xs + rb * (16 * G::PIXB));
+              ldsm_x2_trans(yr, xs + rb * (16 * G::PIXB) + G::CUBE);
+            }
+            uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+            if (MASK) {
+              // pixels 16rb + 4r .. +3 of the tile: even/odd pixel of row 2r, even/odd pixel of row 2r+1
+              const uint32_t vb = *reinterpret_cast<const uint32_t*>(pl + 16 * rb + 4 * r);
+              m0 = ((vb & DM_VALID_METRICS) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 16)) ? 0xffff0000u : 0u);
+              m1 = ((vb & (DM_VALID_METRICS << 8)) ? 0xffffu : 0u) | ((vb & (DM_VALID_METRICS << 24)) ? 0xffff0000u : 0u);
+              n0 += (m0 & 1u) + (m0 >> 31);
+              n1 += (m1 & 1u) + (m1 >> 31);
+            }
+            // data-range scan on the raw reference words (unmasked); a short last warp re-reads its
+            // last chunk in the unused matrices, which changes neither an OR nor a maximum
 #pragma unroll
-              for (int j = 0; j < MPW; j += 2) orbits |= xr[j] | xr[j + 1];
+            for (int j = 0; j < MPW; j += 2) orbits |= xr[j] | xr[j + 1];
 #pragma unroll
-              for (int j = 0; j < MPW; ++j) { xr[j] ^= OFS; yr[j] ^= OFS; }
+            for (int j = 0; j < MPW; ++j) { xr[j] ^= OFS; yr[j] ^= OFS; }
 #pragma unroll
-              for (int j = 0; j < MPW; j += 2) {
-                umax = __vimax3_u16x2(umax, xr[j], xr[j + 1]);
-                if (DT == DM_I16) umin = __vimin3_u16x2(umin, xr[j], xr[j + 1]);
-                if (!TRACK) ymax = __vimax3_u16x2(ymax, yr[j], yr[j + 1]);
-              }
+            for (int j = 0; j < MPW; j += 2) {
+              umax = __vimax3_u16x2(umax, xr[j], xr[j + 1]);
+              if (DT == DM_I16) umin = __vimin3_u16x2(umin, xr[j], xr[j + 1]);
+              if (!TRACK) ymax = __vimax3_u16x2(ymax, yr[j], yr[j + 1]);
+            }
 #pragma unroll
-              for (int j = 0; j < NM; ++j) {
-                uint32_t x = xr[j], y = yr[j];
-                if (MASK) { const uint32_t m = par_of(j) ? m1 : m0; x &= m; y &= m; }
-                band_word<true, TRACK>(a[j], x, y, maxsel_u);
-                if (DT == DM_I16) {
-                  // max |v| with np.abs semantics (abs(-32768) wraps and never wins) from offset-binary
-                  // extremes: maxsel_u tracks max u (in band_word); here min over u > 0 as min of u-1
-                  // with per-half wrap (u = 0, i.e. -32768 or a masked sample, becomes 0xffff and drops out)
-                  minsel_m1 = vminu2(minsel_m1, vadd2_wrap(vminu2(x, y), 0xffffffffu));
-                }
+            for (int j = 0; j < NM; ++j) {
+              uint32_t x = xr[j], y = yr[j];
+              if (MASK) { const uint32_t m = par_of(j) ? m1 : m0; x &= m; y &= m; }
+              band_word<true, TRACK>(a[j], x, y, maxsel_u);
+              if (DT == DM_I16) {
+                // max |v| with np.abs semantics (abs(-32768) wraps and never wins) from offset-binary
+                // extremes: maxsel_u tracks max u (in band_word); here min over u > 0 as min of u-1
+                // with per-half wrap (u = 0, i.e. -32768 or a masked sample, becomes 0xffff and drops out)
+                minsel_m1 = vminu2(minsel_m1, vadd2_wrap(vminu2(x, y), 0xffffffffu));
               }
             }
           }
-          __syncwarp();
-          if (lane == 0) release_tile(it);
         }
+        __syncwarp();
+        if (lane == 0) {
+          // release_tile(it) with the stage known: arrive on the stage's empty barrier; the arrival that completes the
+          // phase refills the stage with tile it + kStages
+          const uint32_t eb = empty0 + 8u * (uint32_t)S;
+          if (mbar_arrive_is_last_a(eb)) {
+            mbar_wait_a(eb, par, poll_ns);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_tile(it + kStages);
+          }
+        }
+      };
+      for (int it0 = 0; it0 < my_tiles; it0 += EPOCH) {
+        const int it1 = it0 + EPOCH < my_tiles ? it0 + EPOCH : my_tiles;
+        int it = it0;
+        [[maybe_unused]] uint32_t par = (uint32_t)(it0 / kStages) & 1u;
+        // The unrolled form pays where the tile body is small (the plain 23-band-warp build: 132.9 -> 131.4 us per
+        // step); with the masked / four-matrix bodies four copies of it overflow the instruction cache (the int16 scan
+        // build went from 186 to 249 us), so those keep the rolled loop.
+        if constexpr (MPW == 2 && !MASK) {
+          for (; it + kStages <= it1; it += kStages, par ^= 1u) {
+            tile(std::integral_constant<int, 0>(), it, par);
+            tile(std::integral_constant<int, 1>(), it + 1, par);
+            tile(std::integral_constant<int, 2>(), it + 2, par);
+            tile(std::integral_constant<int, 3>(), it + 3, par);
+          }
+        }
+        for (; it < it1; ++it) tile(it & (kStages - 1), it, (uint32_t)(it / kStages) & 1u);
         spill();
       }
     };
+    // (only two counts occur: MPW, and what is left for the last band warp)
+    constexpr int LAST_NM = G::CHUNKS - MPW * (G::BAND_WARPS - 1);
     if (nmat == MPW) run(std::integral_constant<int, MPW>());
-    else if (MPW == 4 && nmat == 3) run(std::integral_constant<int, MPW == 4 ? 3 : 1>());
-    else if (MPW == 4 && nmat == 2) run(std::integral_constant<int, MPW == 4 ? 2 : 1>());
-    else run(std::integral_constant<int, 1>());
+    else run(std::integral_constant<int, LAST_NM>());
 
     // ---- flush: per-band maxima and counts -> shared, then one thread per band -> global
     // (the preceding launch must have finished before anything global is written: no-op unless this
