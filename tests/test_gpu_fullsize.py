@@ -212,3 +212,69 @@ def test_chained_launches_accumulate_exactly():
         evaluate(pair, Want(stats=True, sam=True, err8_caps=(255, 32) if k % 2 else (None, None)), out=P2)
     h2 = P2.to_host()
     assert np.array_equal(h2.isum[:B * 8], 6 * one.isum[:B * 8])
+
+
+def test_case_b_cube_fp64_metrics_strips_sum_to_whole_and_one_strip_matches_oracle():
+    """configs[1] / [4] at FULL size for the float64 kernels (SAM, SID, Sobel-LMSE): the oracle needs about a minute
+    for a 1024 x 1024 x 180 cube, so (a) the whole cube in one launch must equal the sum over eight 128-row strips
+    evaluated one by one (halo row for the stencil), i.e. the grid-stride / prefetching paths at 9 472 warps x 110
+    pixels agree with launches of the size the oracle checks elsewhere, and (b) ONE of those strips, taken as an image
+    of its own, is compared with the oracle directly (131 072 pixels of the full-size data)."""
+    import torch
+    from image_compression_analysis_b200 import finish
+    from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
+    from oracle import distortion_oracle as orc
+    B, H, W = 180, 1024, 1024
+    pair = _pair(B, H, W, "bip", seed=21)
+    want = Want(stats=False, sam=True, sid=True, lmse=True)
+    whole = evaluate(pair, want).to_host()
+    acc = Partials.allocate(B, 0, pair.ref.device, "uint16")
+    n = 8
+    for k in range(n):
+        r0, r1 = H * k // n, H * (k + 1) // n
+        b0, b1 = max(0, r0 - 1), min(H, r1 + 1)
+        core = DevicePair(pair.ref[r0:r1], pair.tst[r0:r1], "uint16", "bip", B, r1 - r0, W)
+        evaluate(core, Want(stats=False, sam=True, sid=True), out=acc)
+        buf = DevicePair(pair.ref[b0:b1], pair.tst[b0:b1], "uint16", "bip", B, b1 - b0, W, None, None, b0, H)
+        evaluate(buf, Want(stats=False, lmse=True), out=acc, rows=(r0 - b0, r1 - b0))
+    torch.cuda.synchronize()
+    parts = acc.to_host()
+    assert parts.spec[2] == whole.spec[2] == H * W
+    assert abs(parts.spec[0] - whole.spec[0]) <= 1e-11 * abs(whole.spec[0])          # sum of arccos
+    assert abs(parts.spec[1] - whole.spec[1]) <= 1e-11 * abs(whole.spec[1])          # sum of SID
+    assert np.allclose(parts.lmse, whole.lmse, rtol=1e-11, atol=0)
+    assert whole.spec[1] > 0 and whole.lmse.min() > 0
+    # (b) strip 3 as an image of its own against the oracle
+    r0, r1 = 3 * H // n, 4 * H // n
+    sub = DevicePair(pair.ref[r0:r1].contiguous(), pair.tst[r0:r1].contiguous(), "uint16", "bip", B, r1 - r0, W)
+    h = evaluate(sub, want).to_host()
+    got = finish.finish_spectral(float(h.spec[0]), float(h.spec[1]), float(h.spec[2]), h.lmse, (r1 - r0) * W)
+    a = np.ascontiguousarray(np.moveaxis(sub.ref.cpu().numpy().view(np.uint16), -1, 0))
+    b = np.ascontiguousarray(np.moveaxis(sub.tst.cpu().numpy().view(np.uint16), -1, 0))
+    ref_vals = orc.compute_sam_sid_lmse_caseB(a, b)
+    for k_ in ("sam_deg", "sid", "lmse"):
+        assert abs(got[k_] - ref_vals[k_]) <= 1e-6 * abs(ref_vals[k_]), (k_, got[k_], ref_vals[k_])
+
+
+def test_scene_gaussian_ssim_strips_sum_to_whole():
+    """configs[3] at FULL size for the Gaussian-window SSIM: the 10980 x 10980 x 4 scene in one launch against the sum
+    over five row strips with their 5-row halos (each strip is of the size range the oracle checks in
+    tests/test_gpu_midsize.py); counts exact, sums to 1e-11."""
+    import torch
+    from image_compression_analysis_b200.engine import DevicePair, Partials, Want, evaluate
+    B, H, W = 4, 10980, 10980
+    pair = _pair(B, H, W, "bsq", seed=5, amp=3, top=4090, mul=16)
+    want = Want(stats=False, ssim_gauss=True)
+    whole = evaluate(pair, want, data_range=65535.0).to_host()
+    acc = Partials.allocate(B, 0, pair.ref.device, "uint16")
+    n = 5
+    for k in range(n):
+        r0, r1 = H * k // n, H * (k + 1) // n
+        b0, b1 = max(0, r0 - 5), min(H, r1 + 5)
+        buf = DevicePair(pair.ref[:, b0:b1].contiguous(), pair.tst[:, b0:b1].contiguous(), "uint16", "bsq", B, b1 - b0, W, None, None, b0, H)
+        evaluate(buf, want, out=acc, rows=(r0 - b0, r1 - b0), data_range=65535.0)
+    torch.cuda.synchronize()
+    parts = acc.to_host()
+    assert np.array_equal(parts.ssimw_cnt, whole.ssimw_cnt) and int(whole.ssimw_cnt[0]) == (H - 10) * (W - 10)
+    assert np.allclose(parts.ssimw_sum, whole.ssimw_sum, rtol=1e-11, atol=0)
+    assert np.all(whole.ssimw_sum / whole.ssimw_cnt < 1.0) and np.all(whole.ssimw_sum / whole.ssimw_cnt > 0.5)
