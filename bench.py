@@ -331,6 +331,17 @@ def run_configs(torch, dist, world, rank, local, peak, clocks_mhz):
         torch.cuda._sleep(200_000)
         a.record(); singles[i % NT].launch(); b.record(); b.synchronize()
         lat_dev.append(a.elapsed_time(b) * 1e3)
+    # the same measurement for the same kernel on a 64 x 64 x 4 tile pair (64 KB): the floor of the method (launch, ramp-up,
+    # flush and the two event records), which the 16.8 MB tile's figure has to be read against
+    tiny_r = torch.randint(0, 2040, (B, 64, 64), device=dev, dtype=torch.int16, generator=g) * 16
+    tiny = PreparedStats(DevicePair(tiny_r, tiny_r.clone(), "uint16", "bsq", B, 64, 64), Partials.allocate(B, 0, dev, "uint16"))
+    lat_floor = []
+    for i in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(200_000)
+        a.record(); tiny.launch(); b.record(); b.synchronize()
+        lat_floor.append(a.elapsed_time(b) * 1e3)
+    lat_floor.sort()
     lat_host = []
     pin = torch.empty(outs[0].flat.numel(), dtype=torch.int64).pin_memory()
     for i in range(30):
@@ -349,6 +360,7 @@ def run_configs(torch, dist, world, rank, local, peak, clocks_mhz):
         "pair_by_pair": {"api": "engine.PreparedStats (one dm_fused_stats launch per pair)", "us_per_pair": ms_1 * 1e3 / NT,
                          "GBps": world * NT * tile_bytes / ms_1 / 1e6},
         "single_pair_latency_us": {"device_isolated_launch_median": lat_dev[len(lat_dev) // 2],
+                                   "device_isolated_launch_floor_64x64_tile": lat_floor[len(lat_floor) // 2],
                                    "host_call_to_result_median": lat_host[len(lat_host) // 2],
                                    "note": "device: CUDA events around one launch behind a spin kernel; host: perf_counter around "
                                            "launch + read-back of the partial vector into pinned memory + stream sync"},
