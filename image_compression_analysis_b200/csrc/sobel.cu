@@ -198,26 +198,29 @@ sobel_lmse_bip_kernel(const uint32_t* __restrict__ ref, const uint32_t* __restri
         }
       };
       ColTerms<DT> a0, a1, a2, r0, r1, r2;
-      uint32_t wa[4], wr[4], na[4], nr[4];
-      fetch(c0 - 1, wa, wr); a0.set(wa); r0.set(wr);
-      fetch(c0, wa, wr); a1.set(wa); r1.set(wr);
-      fetch(c0 + 1, wa, wr);                                   // column x+1 of the first output column, in flight
-      // one output column: fetch the column after next first, then consume the fetched one as the window's
-      // right edge (three columns per trip: the window rotates by renaming; a six-column trip that also
-      // renames the raw buffers doubles the code and was 20 % slower)
-#define DM_SOBEL_STEP(L_, C_, R_, x_)                                                   \
+      // Raw words of three columns in flight, one buffer per step of the three-column trip: column c lives in buffer
+      // (c - c0) mod 3, is consumed as the window's right edge one step after ... three steps after its loads were issued
+      // and refilled on the spot with the column three ahead -- the buffers rotate by NAME like the window (no register
+      // copies: 8 moves per step in the one-buffer form), and a load has three steps (~550 instructions) to land (the
+      // one-column lead left 0.94 stall cycles per issued instruction on the scoreboard, profiles/r02f_ncu_lmse.txt).
+      uint32_t wa0[4], wr0[4], wa1[4], wr1[4], wa2[4], wr2[4];
+      fetch(c0 - 1, wa0, wr0); a0.set(wa0); r0.set(wr0);
+      fetch(c0, wa0, wr0); a1.set(wa0); r1.set(wr0);
+      fetch(c0 + 1, wa1, wr1);                                 // right edges of output columns c0, c0 + 1, c0 + 2
+      fetch(c0 + 2, wa2, wr2);
+      fetch(c0 + 3, wa0, wr0);
+#define DM_SOBEL_STEP(L_, C_, R_, x_, B_)                                               \
       do {                                                                              \
-        fetch((x_) + 2, na, nr);                                                        \
-        a##R_.set(wa); r##R_.set(wr);                                                   \
+        a##R_.set(wa##B_); r##R_.set(wr##B_);                                           \
+        fetch((x_) + 4, wa##B_, wr##B_);                                                \
         emit(a##L_, a##C_, a##R_, r##L_, r##C_, r##R_, (x_) < c1);                      \
-        _Pragma("unroll") for (int k = 0; k < 4; ++k) { wa[k] = na[k]; wr[k] = nr[k]; } \
       } while (0)
       // the last trip may run one or two columns past the item: their (clamped) loads are harmless and
       // their terms are dropped -- cheaper than a second copy of the step code for the tail
       for (int x = c0; x < c1; x += 3) {
-        DM_SOBEL_STEP(0, 1, 2, x);
-        DM_SOBEL_STEP(1, 2, 0, x + 1);
-        DM_SOBEL_STEP(2, 0, 1, x + 2);
+        DM_SOBEL_STEP(0, 1, 2, x, 1);
+        DM_SOBEL_STEP(1, 2, 0, x + 1, 2);
+        DM_SOBEL_STEP(2, 0, 1, x + 2, 0);
       }
 #undef DM_SOBEL_STEP
     }
