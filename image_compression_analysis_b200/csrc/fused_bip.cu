@@ -22,6 +22,11 @@
 // A stage is released (empty mbarrier) when every consumer warp that reads it has arrived.  The kernel is
 // persistent: one CTA per SM, tiles strided over CTAs.  Shared-memory reads are conflict free for
 // EnMAP's 180 bands (pixel pitch 45 x 8 B, odd).  See DESIGN.md for the instruction budget.
+//
+// That is the run-time-geometry kernel (fused_bip_kernel, any band count = 0 mod 4 up to 256).  EnMAP's 180 bands take
+// fused_ct_kernel further down: compile-time geometry, no producer warp, ldmatrix-paired band warps, two lanes per
+// pixel in the pixel warps, launches chained by programmatic dependent launch -- and, in its SCAN build
+// (dm_fused_bip_scan), the validity rule of run_codec.py:249-263 evaluated by the pixel warps inside the same pass.
 
 #include <cstdlib>
 #include <type_traits>
@@ -1337,7 +1342,7 @@ namespace {
 // plane is computed in the kernel from the pair's nodata values and the caller's mask).
 struct ScanSpec { const uint8_t* valid_in; uint8_t* plane_out; int64_t* counts; };
 
-int fused_bip_impl(const char* who, const dm_pair_t& p, const uint8_t* plane, const ScanSpec* scan, int64_t* sums, int64_t* maxs,
+int fused_bip_impl(const dm_pair_t& p, const uint8_t* plane, const ScanSpec* scan, int64_t* sums, int64_t* maxs,
                    uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
                    const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
                    double* spectral_acc, void* workspace, cudaStream_t s) {
@@ -1353,7 +1358,6 @@ int fused_bip_impl(const char* who, const dm_pair_t& p, const uint8_t* plane, co
   if (err8_g && (!lut_g || cap_g < 0 || cap_g > 65535)) return fail(DM_EARG, "dm_fused_bip: bad global LUT");
   if (err8_z && (!lut_z || cap_z < 0 || cap_z > 65535)) return fail(DM_EARG, "dm_fused_bip: bad zoom LUT");
   if (want_sam && (!spectral_acc || !workspace)) return fail(DM_EARG, "dm_fused_bip: spectral_acc / workspace is null");
-  (void)who;
   FusedArgs g;
   g.ref = p.ref; g.tst = p.tst; g.plane = plane; g.npix = p.rows * p.width; g.bands = (int)B;
   g.P = 0; g.ntiles = 0; g.tail_pixels = 0; g.zero = 0;
@@ -1417,7 +1421,7 @@ int launch_fused_bip(const dm_pair_t& p, const uint8_t* plane, int64_t* sums, in
                      uint16_t* errmax_out, const uint8_t* lut_g, int cap_g, uint8_t* err8_g, int64_t* hist8_g,
                      const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
                      double* spectral_acc, void* workspace, cudaStream_t s) {
-  return fused_bip_impl("dm_fused_bip", p, plane, nullptr, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
+  return fused_bip_impl(p, plane, nullptr, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
                         lut_z, cap_z, err8_z, hist8_z, want_sam, spectral_acc, workspace, s);
 }
 
@@ -1427,7 +1431,7 @@ int launch_fused_bip_scan(const dm_pair_t& p, const uint8_t* valid_in, uint8_t* 
                           const uint8_t* lut_z, int cap_z, uint8_t* err8_z, int64_t* hist8_z, int want_sam,
                           double* spectral_acc, void* workspace, cudaStream_t s) {
   const ScanSpec sc{valid_in, plane_out, counts};
-  return fused_bip_impl("dm_fused_bip_scan", p, nullptr, &sc, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
+  return fused_bip_impl(p, nullptr, &sc, sums, maxs, errmax_out, lut_g, cap_g, err8_g, hist8_g,
                         lut_z, cap_z, err8_z, hist8_z, want_sam, spectral_acc, workspace, s);
 }
 
